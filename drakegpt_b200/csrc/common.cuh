@@ -1,0 +1,109 @@
+// Shared device/host helpers for the drakegpt_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/drakegpt_b200.h"
+
+namespace dgpt {
+
+// ---------------------------------------------------------------------------
+// error plumbing (thread-local message, negative return codes)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+int require_device();
+
+#define DGPT_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      dgpt::set_error(__VA_ARGS__);    \
+      return DGPT_E_ARG;               \
+    }                                  \
+  } while (0)
+
+#define DGPT_DEVICE_OR_RETURN()            \
+  do {                                     \
+    int _rc = dgpt::require_device();      \
+    if (_rc != 0) return _rc;              \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10, the one dropout / sampling RNG of the library.
+// ---------------------------------------------------------------------------
+struct u32x4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
+// four consecutive elements [4*q, 4*q+3] of a dropout site share one Philox call
+__host__ __device__ __forceinline__ u32x4 dropout_bits4(uint64_t seed, uint32_t site, uint64_t quad) {
+  return philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), site, 0x44524b45u /* "DRKE" */,
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  // keep iff bits >= threshold; P(drop) = threshold / 2^32
+  double t = (double)p * 4294967296.0;
+  if (t < 0.0) t = 0.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+__host__ __device__ __forceinline__ uint32_t pick4(const u32x4& r, int lane) {
+  return lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+}
+
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t index,
+                                                      uint32_t threshold) {
+  const u32x4 r = dropout_bits4(seed, site, index >> 2);
+  return pick4(r, (int)(index & 3)) >= threshold;
+}
+
+// ---------------------------------------------------------------------------
+// typed loads / stores for the two activation types
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dgpt

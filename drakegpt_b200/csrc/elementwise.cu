@@ -1,0 +1,578 @@
+// HBM-bound kernels of the training step: embedding gather/scatter, LayerNorm
+// forward/backward (+fused residual-grad add and dropout-masked bf16 copy),
+// cross-entropy forward+backward, flat AdamW, dropout/cast, column sums and the
+// on-device sampler.  All are grid-sized in multiples of the SM count or one
+// warp per row with float4 accesses; none allocates or synchronises.
+#include "common.cuh"
+
+namespace dgpt {
+
+static constexpr int kSMs = 148;
+
+// ---------------------------------------------------------------------------
+// dropout_scale / cast
+// ---------------------------------------------------------------------------
+template <typename OutT>
+__global__ void dropout_scale_kernel(const float* __restrict__ in, const float* __restrict__ aux,
+                                     OutT* __restrict__ out, int64_t n,
+                                     uint32_t thr, float inv_keep, uint64_t seed,
+                                     const uint64_t* __restrict__ seed_dev, uint32_t site) {
+  if (thr && seed_dev) seed += *seed_dev;
+  const int64_t nq = (n + 3) >> 2;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = q << 2;
+    u32x4 r = u32x4{~0u, ~0u, ~0u, ~0u};
+    if (thr) r = dropout_bits4(seed, site, (uint64_t)q);
+    if (i0 + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(in + i0);
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (pick4(r, j) >= thr) ? o[j] * inv_keep : 0.f;
+      if (aux) {
+        const float4 a = *reinterpret_cast<const float4*>(aux + i0);
+        if (!(a.x > 0.f)) o[0] = 0.f;
+        if (!(a.y > 0.f)) o[1] = 0.f;
+        if (!(a.z > 0.f)) o[2] = 0.f;
+        if (!(a.w > 0.f)) o[3] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[i0 + j] = from_f32<OutT>(o[j]);
+    } else {
+      for (int j = 0; j < 4 && i0 + j < n; ++j)
+        out[i0 + j] = from_f32<OutT>(((pick4(r, j) >= thr) && (!aux || aux[i0 + j] > 0.f)) ? in[i0 + j] * inv_keep : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// embedding
+// ---------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ tok,
+                                 const float* __restrict__ pos, float* __restrict__ x, int M, int T,
+                                 int C, int pos_offset) {
+  const int64_t total = (int64_t)M * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / C), c = (int)(i - (int64_t)m * C);
+    const int t = m % T;
+    float v = tok[idx[m] * (int64_t)C + c];
+    if (pos) v += pos[(int64_t)(t + pos_offset) * C + c];
+    x[i] = v;
+  }
+}
+
+// dpos[t,c] += sum_b dx[b,t,c]  (deterministic: fixed summation order over b)
+__global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B,
+                                     int T, int C, int pos_offset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * C) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += dx[(int64_t)b * T * C + i];
+  dpos[(int64_t)pos_offset * C + i] += acc;
+}
+
+// dtok[v, c0:c0+128] += sum_{m: idx[m]==v} dx[m, c]; one CTA per (v, column chunk).
+// The 80-row table would serialise global atomics, so each CTA scans idx, builds
+// an ordered list of matching rows in shared memory and reduces them itself.
+__global__ void __launch_bounds__(128) embed_bwd_tok_kernel(const int64_t* __restrict__ idx,
+                                                            const float* __restrict__ dx,
+                                                            float* __restrict__ dtok, int M, int C) {
+  __shared__ int list[128];
+  __shared__ int warp_cnt[4];
+  const int v = blockIdx.x;
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (int base = 0; base < M; base += 128) {
+    const int m = base + threadIdx.x;
+    const bool hit = (m < M) && (idx[m] == (int64_t)v);
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < w) off += warp_cnt[i];
+      total += warp_cnt[i];
+    }
+    if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = m;
+    __syncthreads();
+    if (c < C)
+      for (int j = 0; j < total; ++j) acc += dx[(int64_t)list[j] * C + c];
+    __syncthreads();
+  }
+  if (c < C) dtok[(int64_t)v * C + c] += acc;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row kept in registers (C <= 32*4*kMaxV)
+// ---------------------------------------------------------------------------
+static constexpr int kMaxV = 8;  // float4 per lane -> C <= 1024 on the register path
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x,
+                                                     const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta,
+                                                     OutT* __restrict__ y, float* __restrict__ mean,
+                                                     float* __restrict__ rstd, int M, int C,
+                                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + (int64_t)row * C;
+  OutT* yr = y + (int64_t)row * C;
+  if (gamma == nullptr) {  // identity cast
+    for (int c = lane; c < C; c += 32) yr[c] = from_f32<OutT>(xr[c]);
+    return;
+  }
+  if ((C & 3) == 0 && C <= 128 * kMaxV) {
+    const int nv = C >> 2;
+    float4 r[kMaxV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        r[i] = reinterpret_cast<const float4*>(xr)[q];
+        s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+      }
+    }
+    const float mu = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        const float a = r[i].x - mu, b = r[i].y - mu, c = r[i].z - mu, d = r[i].w - mu;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(ss) / (float)C + eps);
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[q];
+        const float4 b = reinterpret_cast<const float4*>(beta)[q];
+        const float o0 = (r[i].x - mu) * rs * g.x + b.x, o1 = (r[i].y - mu) * rs * g.y + b.y;
+        const float o2 = (r[i].z - mu) * rs * g.z + b.z, o3 = (r[i].w - mu) * rs * g.w + b.w;
+        if constexpr (sizeof(OutT) == 4) {
+          reinterpret_cast<float4*>(yr)[q] = make_float4(o0, o1, o2, o3);
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(yr)[q] = pk;
+        }
+      }
+    }
+    return;
+  }
+  // generic path
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mu = warp_sum(s) / (float)C;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mu;
+    ss += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(ss) / (float)C + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  for (int c = lane; c < C; c += 32)
+    yr[c] = from_f32<OutT>((xr[c] - mu) * rs * gamma[c] + beta[c]);
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm backward: warp per row (grid-stride), dgamma/dbeta reduced per CTA
+// in shared memory, one global atomic per column per CTA.
+// ---------------------------------------------------------------------------
+template <typename DyT, typename MT>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(
+    const DyT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    MT* __restrict__ dxm, uint32_t thr, float inv_keep, uint64_t seed,
+    const uint64_t* __restrict__ seed_dev, uint32_t site, int M, int C) {
+  extern __shared__ float sm[];  // [2*C]: dgamma, dbeta partials
+  if (thr && seed_dev) seed += *seed_dev;
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    const DyT* dyr = dy + (int64_t)row * C;
+    const float* xr = x + (int64_t)row * C;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = to_f32(dyr[c]);
+      const float xh = (xr[c] - mu) * rs;
+      const float dxh = d * gamma[c];
+      s1 += dxh;
+      s2 += dxh * xh;
+      atomicAdd(&sg[c], d * xh);
+      atomicAdd(&sb[c], d);
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mu) * rs;
+      float v = rs * (to_f32(dyr[c]) * gamma[c] - s1 - xh * s2);
+      const int64_t i = (int64_t)row * C + c;
+      if (dres) v += dres[i];
+      dx[i] = v;
+      if (dxm) {
+        const bool keep = thr == 0 || dropout_keep(seed, site, (uint64_t)i, thr);
+        dxm[i] = from_f32<MT>(keep ? v * inv_keep : 0.f);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// cross-entropy forward + backward, warp per row
+// ---------------------------------------------------------------------------
+template <typename DlT>
+__global__ void __launch_bounds__(256) cross_entropy_kernel(
+    const float* __restrict__ logits, int ld, const int64_t* __restrict__ targets,
+    float* __restrict__ loss_sum, DlT* __restrict__ dlogits, int ld_dl,
+    const float* __restrict__ dloss, int M, int V) {
+  __shared__ float part[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int row = blockIdx.x * (blockDim.x >> 5) + w;
+  float row_loss = 0.f;
+  if (row < M) {
+    const float* lr = logits + (int64_t)row * ld;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, lr[v]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int v = lane; v < V; v += 32) se += expf(lr[v] - mx);
+    se = warp_sum(se);
+    const int tgt = (int)targets[row];
+    row_loss = (logf(se) + mx - lr[tgt]) / (float)M;
+    if (dlogits) {
+      const float scale = (dloss ? dloss[0] : 1.f) / (float)M;
+      const float inv = 1.f / se;
+      DlT* dr = dlogits + (int64_t)row * ld_dl;
+      for (int v = lane; v < V; v += 32) {
+        const float p = expf(lr[v] - mx) * inv;
+        dr[v] = from_f32<DlT>((p - (v == tgt ? 1.f : 0.f)) * scale);
+      }
+    }
+  }
+  if (lane == 0) part[w] = row_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+    atomicAdd(loss_sum, s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// flat AdamW
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    __nv_bfloat16* __restrict__ shadow, int64_t n,
+                                                    const float* __restrict__ hyper,
+                                                    const int64_t* __restrict__ step, int zero_grad) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
+  const double t = (double)(*step + 1);
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  const int64_t nq = n >> 2;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[q];
+    const float4 gg = reinterpret_cast<const float4*>(g)[q];
+    float4 mm = reinterpret_cast<float4*>(m)[q];
+    float4 vv = reinterpret_cast<float4*>(v)[q];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = ga[j] * gs;
+      pa[j] *= decay;
+      ma[j] = ma[j] + (gj - ma[j]) * (1.f - b1);
+      va[j] = va[j] * b2 + gj * gj * (1.f - b2);
+      pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[q] = pp;
+    reinterpret_cast<float4*>(m)[q] = mm;
+    reinterpret_cast<float4*>(v)[q] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow)[q] = pk;
+    }
+  }
+  // tail (n % 4)
+  const int64_t i = (nq << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float gj = g[i] * gs;
+    float pj = p[i] * decay;
+    const float mj = m[i] + (gj - m[i]) * (1.f - b1);
+    const float vj = v[i] * b2 + gj * gj * (1.f - b2);
+    pj -= step_size * mj / (sqrtf(vj) * inv_sqrt_bc2 + eps);
+    p[i] = pj; m[i] = mj; v[i] = vj;
+    if (zero_grad) g[i] = 0.f;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pj);
+  }
+}
+
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) { *ctr += delta; }
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                 int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// ---------------------------------------------------------------------------
+// column sums (bias gradients): 32 columns x 8 row-lanes per CTA
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int M, int N, int ldx,
+                                                     float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float acc = 0.f;
+  if (col < N)
+    for (int r = r0 + ty; r < r1; r += 8) acc += to_f32(X[(int64_t)r * ldx + col]);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    atomicAdd(&out[col], s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// sampler: one warp per sequence
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) sample_kernel(const float* __restrict__ logits, int ld,
+                                                    int64_t* __restrict__ seq, int64_t seq_ld, int pos,
+                                                    int V, int greedy, uint64_t seed, uint32_t step) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const float* lr = logits + (int64_t)b * ld;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int v = lane; v < V; v += 32) {
+    const float l = lr[v];
+    if (l > mx) { mx = l; arg = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  int choice = arg;
+  if (!greedy) {
+    float se = 0.f;
+    for (int v = lane; v < V; v += 32) se += expf(lr[v] - mx);
+    se = warp_sum(se);
+    const u32x4 r = philox4x32_10((uint32_t)b, step, 0x53414d50u /* "SAMP" */, 0u, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+    const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * se;  // target mass in (0, se)
+    // inverse CDF in vocabulary order, 32 tokens per sweep
+    float base = 0.f;
+    choice = V - 1;
+    bool done = false;
+    for (int v0 = 0; v0 < V && !done; v0 += 32) {
+      const int v = v0 + lane;
+      const float e = v < V ? expf(lr[v] - mx) : 0.f;
+      float c = e;  // inclusive scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o) c += t;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, v < V && base + c > u);
+      if (hit) {
+        choice = v0 + __ffs(hit) - 1;
+        done = true;
+      }
+      base += __shfl_sync(0xffffffffu, c, 31);
+    }
+  }
+  if (lane == 0) seq[(int64_t)b * seq_ld + pos] = (int64_t)choice;
+}
+
+}  // namespace dgpt
+
+using namespace dgpt;
+
+extern "C" {
+
+int dgpt_dropout_scale(const float* in, const float* relu_aux, void* out, int out_dtype, int64_t n, float p,
+                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  DGPT_REQUIRE(p >= 0.f && p < 1.f, "dropout_scale: p=%f out of [0,1)", p);
+  if (n == 0) return DGPT_OK;
+  const uint32_t thr = dropout_threshold(p);
+  const float inv_keep = 1.f / (1.f - p);
+  const int grid = (int)min((int64_t)kSMs * 8, (n / 4 + 255) / 256 + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == DGPT_F32)
+    dropout_scale_kernel<float><<<grid, 256, 0, st>>>(in, relu_aux, (float*)out, n, thr, inv_keep, seed, seed_dev, site);
+  else
+    dropout_scale_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, st>>>(in, relu_aux, (__nv_bfloat16*)out, n, thr, inv_keep, seed, seed_dev, site);
+  return check_launch("dropout_scale");
+}
+
+int dgpt_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (n == 0) return DGPT_OK;
+  const int grid = (int)min((int64_t)kSMs * 8, (n + 255) / 256);
+  cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  return check_launch("cast_bf16");
+}
+
+int dgpt_embed_fwd(const int64_t* idx, const float* tok, const float* pos, float* x, int B, int T,
+                   int C, int V, int pos_offset, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  DGPT_REQUIRE(B >= 0 && T >= 0 && C > 0 && V > 0, "embed_fwd: bad shape B=%d T=%d C=%d V=%d", B, T, C, V);
+  const int64_t total = (int64_t)B * T * C;
+  if (total == 0) return DGPT_OK;
+  const int grid = (int)min((int64_t)kSMs * 8, (total + 255) / 256);
+  embed_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, tok, pos, x, B * T, T, C, pos_offset);
+  return check_launch("embed_fwd");
+}
+
+int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos, int B, int T, int C,
+                   int V, int pos_offset, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if ((int64_t)B * T == 0) return DGPT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dpos) embed_bwd_pos_kernel<<<ceil_div((int64_t)T * C, 256), 256, 0, st>>>(dx, dpos, B, T, C, pos_offset);
+  dim3 grid(V, ceil_div(C, 128));
+  embed_bwd_tok_kernel<<<grid, 128, 0, st>>>(idx, dx, dtok, B * T, C);
+  return check_launch("embed_bwd");
+}
+
+int dgpt_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                float* mean, float* rstd, int M, int C, float eps, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (M == 0) return DGPT_OK;
+  DGPT_REQUIRE(C > 0, "ln_fwd: C=%d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(M, 8);
+  if (y_dtype == DGPT_F32)
+    ln_fwd_kernel<float><<<grid, 256, 0, st>>>(x, gamma, beta, (float*)y, mean, rstd, M, C, eps);
+  else
+    ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, C, eps);
+  return check_launch("ln_fwd");
+}
+
+int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                void* dxm, int dxm_dtype, float p, uint64_t seed, const uint64_t* seed_dev,
+                uint32_t site, int M, int C, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (M == 0) return DGPT_OK;
+  DGPT_REQUIRE(C > 0 && C <= 6000, "ln_bwd: C=%d unsupported", C);
+  DGPT_REQUIRE(p >= 0.f && p < 1.f, "ln_bwd: p=%f", p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = min(ceil_div(M, 8), kSMs * 4);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  const uint32_t thr = dropout_threshold(p);
+  const float ik = 1.f / (1.f - p);
+#define LN_BWD(DyT, MT)                                                                             \
+  ln_bwd_kernel<DyT, MT><<<grid, 256, smem, st>>>((const DyT*)dy, x, gamma, mean, rstd, dres, dx,   \
+                                                  dgamma, dbeta, (MT*)dxm, thr, ik, seed, seed_dev, site, M, C)
+  if (dy_dtype == DGPT_F32 && dxm_dtype == DGPT_F32) LN_BWD(float, float);
+  else if (dy_dtype == DGPT_F32) LN_BWD(float, __nv_bfloat16);
+  else if (dxm_dtype == DGPT_F32) LN_BWD(__nv_bfloat16, float);
+  else LN_BWD(__nv_bfloat16, __nv_bfloat16);
+#undef LN_BWD
+  return check_launch("ln_bwd");
+}
+
+int dgpt_cross_entropy(const float* logits, int ld, const int64_t* targets, float* loss_sum,
+                       void* dlogits, int dl_dtype, int ld_dl, const float* dloss, int M, int V,
+                       void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (M == 0) return DGPT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(M, 8);
+  if (dl_dtype == DGPT_F32)
+    cross_entropy_kernel<float><<<grid, 256, 0, st>>>(logits, ld, targets, loss_sum, (float*)dlogits, ld_dl, dloss, M, V);
+  else
+    cross_entropy_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(logits, ld, targets, loss_sum, (__nv_bfloat16*)dlogits, ld_dl, dloss, M, V);
+  return check_launch("cross_entropy");
+}
+
+int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
+  return check_launch("counter_add");
+}
+
+int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n, const float* hyper,
+               int64_t* step, int zero_grad, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (n == 0) return DGPT_OK;
+  DGPT_REQUIRE(hyper && step, "adamw: hyper/step must not be NULL");
+  DGPT_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 &&
+                   (((uintptr_t)shadow) & 7) == 0,
+               "adamw: arenas must be 16-byte aligned");
+  const int grid = (int)min((int64_t)kSMs * 8, (n / 4 + 255) / 256 + 1);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, hyper, step, zero_grad);
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint64_t*>(step), 1ull);
+  return check_launch("adamw");
+}
+
+int dgpt_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, int accumulate,
+                void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (N == 0) return DGPT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
+  if (M == 0) return DGPT_OK;
+  const int gy = max(1, min(ceil_div(M, 64), (kSMs * 4) / max(1, ceil_div(N, 32))));
+  const int rows_per_cta = ceil_div(M, gy);
+  dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
+  if (dtype == DGPT_F32)
+    colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)X, M, N, ldx, out, rows_per_cta);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out, rows_per_cta);
+  return check_launch("colsum");
+}
+
+int dgpt_sample(const float* logits, int ld, int64_t* seq, int64_t seq_ld, int pos, int B, int V,
+                int greedy, uint64_t seed, uint32_t step, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  if (B == 0) return DGPT_OK;
+  sample_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(logits, ld, seq, seq_ld, pos, V, greedy, seed, step);
+  return check_launch("sample");
+}
+
+}  // extern "C"

@@ -1,0 +1,484 @@
+"""Fused runner for the DrakeGPT language models: forward / backward / AdamW / decode
+as explicit kernel sequences over preallocated buffers (no autograd tape).
+
+This is the hot path behind ``TransformerLM`` (training step, evaluation and
+KV-cached generation) and the generation path of the five smaller models.  One
+``Runner`` owns
+
+  * the model's flat parameter arena (``optim.FlatParams``) and, in tensor mode,
+    the bf16 weight shadows the tcgen05 GEMMs read;
+  * per-(B,T) activation workspaces, allocated once so that the whole step is
+    CUDA-graph capturable;
+  * the kernel schedule.  Per ResidualBlock2 layer (src/model_component.py:505-506):
+        forward   LN1 -> packed-QKV GEMM -> fused causal attention ->
+                  proj GEMM (+bias +dropout +residual) -> LN2 ->
+                  FFN1 GEMM (+bias +ReLU) -> FFN2 GEMM (+bias +dropout +residual)
+        backward  the mirror image: wgrad/dgrad GEMMs fed directly from the
+                  row-major activations (MN-major operands), ReLU mask applied in
+                  the dgrad epilogue, LN backward fused with the residual-gradient
+                  add and the dropout-masked bf16 copy the next GEMM consumes.
+
+Modes: ``"fp32"`` = exact CUDA-core kernels (any model / shape; parity runs),
+``"bf16"`` = tcgen05 tensor-core GEMMs with bf16 operands, fp32 accumulation and an
+fp32 residual stream (TransformerLM shapes with C % 64 == 0).
+"""
+import torch
+
+from . import ops
+from ._lib import MAJOR_K, MAJOR_MN, KernelError
+from .optim import FlatParams, FusedAdamW
+
+
+def _spec_from_model(model):
+    """Describe any of the six LMs as (embeddings, list of block descriptors, head)."""
+    kind = type(model).__name__
+    names = {id(p): n for n, p in model.named_parameters()}
+
+    def nm(p):
+        return None if p is None else names[id(p)]
+
+    spec = {"kind": kind, "tok": nm(model.token_embedding_table.weight), "pos": None, "layers": [], "lm": None,
+            "ctx": getattr(model, "context_length", None)}
+    if kind == "BigramLM":
+        return spec
+    spec["pos"] = nm(model.position_embedding_table.weight)
+    spec["lm"] = (nm(model.lm_head.weight), nm(model.lm_head.bias))
+
+    def attn_part(m):
+        return {"qkv": nm(m.qkv), "NH": m.num_heads, "H": m.head_size, "p_attn": m.attn_dropout}
+
+    if kind in ("SingleHeadAttentionLM", "MultiHeadAttentionLM"):
+        d = attn_part(model.sa_head)
+        d.update(ln1=None, ln2=None, proj=None, ffn=None, residual=False, p=0.0)
+        spec["layers"].append(d)
+        return spec
+    for blk in model.blocks:
+        d = attn_part(blk.sa_head)
+        d.update(ln1=None, ln2=None, proj=None, ffn=None, residual=False, p=0.0)
+        if hasattr(blk.sa_head, "proj"):
+            d["proj"] = (nm(blk.sa_head.proj.weight), nm(blk.sa_head.proj.bias))
+            d["residual"] = True
+        net = blk.ffwd.net
+        if len(net) == 2:
+            d["ffn"] = ("relu", nm(net[0].weight), nm(net[0].bias))
+        else:
+            d["ffn"] = ("mlp", nm(net[0].weight), nm(net[0].bias), nm(net[2].weight), nm(net[2].bias))
+        if hasattr(blk, "ln1"):
+            d["ln1"] = (nm(blk.ln1.weight), nm(blk.ln1.bias))
+            d["ln2"] = (nm(blk.ln2.weight), nm(blk.ln2.bias))
+            d["p"] = float(blk.ffwd.net[3].p)
+        spec["layers"].append(d)
+    return spec
+
+
+class Runner:
+    def __init__(self, model, mode="fp32"):
+        if mode not in ("fp32", "bf16"):
+            raise ValueError("mode must be 'fp32' or 'bf16'")
+        self.model = model
+        self.mode = mode
+        self.spec = _spec_from_model(model)
+        if mode == "bf16":
+            ok = self.spec["kind"] == "TransformerLM" and all(
+                l["H"] % 8 == 0 and (l["NH"] * l["H"]) % 8 == 0 for l in self.spec["layers"])
+            C = model.token_embedding_table.weight.shape[1]
+            if not ok or C % 8 != 0:
+                raise KernelError("bf16 tensor-core mode needs a TransformerLM with embedding_dim % 8 == 0")
+        self.at = torch.float32 if mode == "fp32" else torch.bfloat16
+        frozen = ("ln_f.",) if self.spec["kind"] == "TransformerLM" else ()
+        self.flat = FlatParams(model, frozen=frozen, with_shadow=(mode == "bf16"))
+        self.device = self.flat.device
+        self._ws = {}
+        self.seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self.base_seed = 0
+        self.opt = None
+        self._cache = None
+
+    # ------------------------------------------------------------------ #
+    # plumbing
+    # ------------------------------------------------------------------ #
+    def _reattach(self):
+        if not self.flat.is_attached():
+            frozen = ("ln_f.",) if self.spec["kind"] == "TransformerLM" else ()
+            old = self.flat
+            self.flat = FlatParams(self.model, frozen=frozen, with_shadow=(self.mode == "bf16"))
+            if old.p.device == self.flat.p.device and old.n_live == self.flat.n_live:
+                self.flat.m.copy_(old.m)
+                self.flat.v.copy_(old.v)
+            if self.opt is not None:
+                self.opt.flat = self.flat
+            self.device = self.flat.device
+            self._ws = {}
+
+    def buf(self, key, shape, dtype=None, zero=False):
+        dtype = self.at if dtype is None else dtype
+        k = (key, tuple(shape), dtype)
+        t = self._ws.get(k)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)
+            self._ws[k] = t
+        return t
+
+    def w(self, name):
+        """Weight as a GEMM operand: fp32 master (exact mode) or bf16 shadow (tensor mode)."""
+        return self.flat.view(name) if self.mode == "fp32" else self.flat.shadow_of(name)
+
+    def f(self, name):
+        return None if name is None else self.flat.view(name)
+
+    def g(self, name):
+        return self.flat.grad(name)
+
+    def _drop(self, p, site, training):
+        if not training or p <= 0.0:
+            return None
+        return ops.Dropout(p, self.base_seed, site, self.seed_dev)
+
+    def _gemm(self, *a, **k):
+        return ops.raw_gemm(*a, **k)
+
+    # ------------------------------------------------------------------ #
+    # forward
+    # ------------------------------------------------------------------ #
+    def forward(self, idx, targets=None, training=False, save=False, want_logits=True):
+        """Full-sequence forward.  Returns (logits (B*T,V) fp32, loss 0-d tensor or None).
+
+        ``save=True`` keeps every activation the backward pass needs in the
+        workspace keyed by layer.
+        """
+        self._reattach()
+        self.flat.refresh_shadow()
+        sp = self.spec
+        B, T = idx.shape
+        M = B * T
+        idx = idx.contiguous()
+        tok = self.f(sp["tok"])
+        V = tok.shape[0]
+        if sp["kind"] == "BigramLM":
+            logits = self.buf("logits", (M, V), torch.float32)
+            ops.raw_embed_fwd(idx, tok, None, logits.view(B, T, V))
+        else:
+            C = tok.shape[1]
+            if sp["ctx"] is not None and T > sp["ctx"]:
+                raise KernelError(f"sequence length {T} exceeds context_length {sp['ctx']}")
+            x = self.buf("x0", (M, C), torch.float32)
+            ops.raw_embed_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C))
+            for li, L in enumerate(sp["layers"]):
+                x = self._layer_fwd(li, L, x, B, T, training, save)
+            xin = x
+            if xin.dtype != self.at:
+                xin = ops.raw_dropout_scale(x, self.buf("x_last_at", x.shape))
+            self._x_last = xin
+            logits = self.buf("logits", (M, V), torch.float32)
+            self._gemm(xin, self.w(sp["lm"][0]), logits, bias=self.f(sp["lm"][1]))
+        loss = None
+        if targets is not None:
+            loss = self.buf("loss", (1,), torch.float32)
+            loss.zero_()
+            dl = None
+            if save:
+                ldl = (V + 7) // 8 * 8
+                dl = self.buf("dlogits", (M, ldl), self.at, zero=True)
+            ops.raw_cross_entropy(logits, targets.contiguous().view(-1), loss, dl, None, M, V)
+            loss = loss.view(())
+        return logits, loss
+
+    def _layer_fwd(self, li, L, x, B, T, training, save):
+        M, C = x.shape
+        NH, H = L["NH"], L["H"]
+        D = NH * H
+        tag = (lambda n: f"L{li}.{n}") if save else (lambda n: "tmp." + n)
+        if save:
+            self._saved_x = getattr(self, "_saved_x", {})
+        # ---- attention branch ----
+        if L["ln1"] is not None:
+            a = self.buf(tag("xn1"), (M, C))
+            mean1, rstd1 = self.buf(tag("mean1"), (M,), torch.float32), self.buf(tag("rstd1"), (M,), torch.float32)
+            ops.raw_ln_fwd(x, self.f(L["ln1"][0]), self.f(L["ln1"][1]), a, mean1, rstd1)
+        elif x.dtype != self.at:
+            a = ops.raw_dropout_scale(x, self.buf(tag("xn1"), (M, C)))
+        else:
+            a = x
+        qkv = self.buf(tag("qkv"), (M, 3 * D))
+        self._gemm(a, self.w(L["qkv"]).view(3 * D, C), qkv)
+        q3 = qkv.view(B, T, 3 * D)
+        att = self.buf(tag("att"), (M, D))
+        lse = self.buf(tag("lse"), (B, NH, T), torch.float32)
+        ops.raw_attn_fwd(q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:], att.view(B, T, D), lse, NH, H, H ** -0.5,
+                         self._drop(L["p_attn"], 4 * li, training))
+        if L["proj"] is not None:
+            x1 = self.buf(tag("x1"), (M, C), torch.float32)
+            self._gemm(att, self.w(L["proj"][0]), x1, bias=self.f(L["proj"][1]),
+                       dropout=self._drop(L["p"], 4 * li + 1, training), residual=x if L["residual"] else None)
+        else:
+            x1 = att
+        # ---- feed-forward branch ----
+        if L["ffn"] is None:
+            out = x1
+        else:
+            if L["ln2"] is not None:
+                b = self.buf(tag("xn2"), (M, C))
+                mean2 = self.buf(tag("mean2"), (M,), torch.float32)
+                rstd2 = self.buf(tag("rstd2"), (M,), torch.float32)
+                ops.raw_ln_fwd(x1, self.f(L["ln2"][0]), self.f(L["ln2"][1]), b, mean2, rstd2)
+            elif x1.dtype != self.at:
+                b = ops.raw_dropout_scale(x1, self.buf(tag("xn2"), (M, C)))
+            else:
+                b = x1
+            if L["ffn"][0] == "relu":
+                out = self.buf(tag("x2"), (M, C), torch.float32)
+                self._gemm(b, self.w(L["ffn"][1]), out, bias=self.f(L["ffn"][2]), relu=True)
+            else:
+                h = self.buf(tag("h"), (M, self.f(L["ffn"][1]).shape[0]))
+                self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True)
+                out = self.buf(tag("x2"), (M, C), torch.float32)
+                self._gemm(h, self.w(L["ffn"][3]), out, bias=self.f(L["ffn"][4]),
+                           dropout=self._drop(L["p"], 4 * li + 2, training), residual=x1 if L["residual"] else None)
+        if save:
+            self._saved_x[li] = x
+        return out
+
+    # ------------------------------------------------------------------ #
+    # backward (TransformerLM / ResidualBlock2 structure)
+    # ------------------------------------------------------------------ #
+    def backward(self, idx, training=True, reducer=None):
+        """Backward of the last ``forward(..., save=True)``; gradients are ACCUMULATED into the flat arena.
+
+        ``reducer`` (parallel.GradAllReducer built by ``make_reducer``) is told after the lm_head, after
+        every block and after the embeddings that the next gradient bucket is final, so the data-parallel
+        all-reduce of that slice overlaps the rest of the backward pass.
+        """
+        sp = self.spec
+        if sp["kind"] != "TransformerLM":
+            raise KernelError("Runner.backward implements the TransformerLM block structure; smaller models "
+                              "train through the autograd Functions in ops.py")
+        B, T = idx.shape
+        M = B * T
+        tok = self.f(sp["tok"])
+        V, C = tok.shape
+        sm = 148
+        dl = self.buf("dlogits", (M, (V + 7) // 8 * 8), self.at, zero=True)
+        x_last = self._x_last
+        # lm_head: dW = dl^T x, db = colsum(dl), dx = dl W
+        self._gemm(dl, x_last, self.g(sp["lm"][0]), a_major=MAJOR_MN, b_major=MAJOR_MN, M=V, N=C, K=M,
+                   accumulate=True, split_k=self._splits(V, C, M, sm))
+        ops.raw_colsum(dl, self.g(sp["lm"][1]), accumulate=True, M=M, N=V)
+        if reducer is not None:
+            reducer.bucket_ready()
+        gcur = self.buf("g_a", (M, C), torch.float32)
+        self._gemm(dl, self.w(sp["lm"][0]), gcur, b_major=MAJOR_MN, M=M, N=C, K=V)
+        gm = self.buf("gm", (M, C))
+        nl = len(sp["layers"])
+        # masked bf16/fp32 copy of the incoming gradient for the last layer's FFN2
+        Llast = sp["layers"][-1]
+        ops.raw_dropout_scale(gcur, gm, self._drop(Llast["p"], 4 * (nl - 1) + 2, training))
+        galt = self.buf("g_b", (M, C), torch.float32)
+        for li in range(nl - 1, -1, -1):
+            L = sp["layers"][li]
+            nxt = sp["layers"][li - 1] if li > 0 else None
+            gcur = self._layer_bwd(li, L, nxt, gcur, galt, gm, B, T, training)
+            if reducer is not None:
+                reducer.bucket_ready()
+        # embeddings
+        ops.raw_embed_bwd(idx.contiguous(), gcur.view(B, T, C), self.g(sp["tok"]), self.g(sp["pos"]))
+        if reducer is not None:
+            reducer.bucket_ready()
+
+    def make_reducer(self, group=None):
+        """Gradient buckets in the order the backward pass completes them (lm_head, blocks L-1..0, embeddings)."""
+        from .parallel import GradAllReducer, bucket_ranges
+        nl = len(self.spec["layers"])
+        groups = [("lm_head.",)] + [(f"blocks.{i}.",) for i in range(nl - 1, -1, -1)]
+        groups.append(("token_embedding_table.", "position_embedding_table."))
+        red = GradAllReducer(self.flat.g, bucket_ranges(self.flat.slots, self.flat.n_live, groups), group)
+        if self.opt is not None:
+            self.opt.grad_scale = red.grad_scale
+        return red
+
+    @staticmethod
+    def _splits(n_out_rows, n_out_cols, k, sm):
+        tiles = ((n_out_rows + 127) // 128) * ((n_out_cols + 127) // 128)
+        return max(1, min(sm // max(tiles, 1), k // 512))
+
+    def _layer_bwd(self, li, L, nxt, g, g_other, gm, B, T, training):
+        """g: dL/dx_out (fp32), gm: dropout-masked copy of g in the activation dtype.  Returns dL/dx_in."""
+        M, C = g.shape
+        NH, H = L["NH"], L["H"]
+        D = NH * H
+        sm = 148
+        tag = lambda n: f"L{li}.{n}"  # noqa: E731
+        at = self.at
+        F = self.f(L["ffn"][1]).shape[0]
+        x_in = self._saved_x[li]
+        xn1, qkv, att = self.buf(tag("xn1"), (M, C)), self.buf(tag("qkv"), (M, 3 * D)), self.buf(tag("att"), (M, D))
+        lse = self.buf(tag("lse"), (B, NH, T), torch.float32)
+        x1, xn2, h = self.buf(tag("x1"), (M, C), torch.float32), self.buf(tag("xn2"), (M, C)), self.buf(tag("h"), (M, F))
+        mean1, rstd1 = self.buf(tag("mean1"), (M,), torch.float32), self.buf(tag("rstd1"), (M,), torch.float32)
+        mean2, rstd2 = self.buf(tag("mean2"), (M,), torch.float32), self.buf(tag("rstd2"), (M,), torch.float32)
+        # ---- FFN2: y = h W2^T + b2 (dropout, residual) ----
+        self._gemm(gm, h, self.g(L["ffn"][3]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
+                   split_k=self._splits(C, F, M, sm))
+        ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
+        dh = self.buf("dh", (M, F))
+        self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN, relu_aux=h)
+        # ---- FFN1: h = relu(xn2 W1^T + b1) ----
+        self._gemm(dh, xn2, self.g(L["ffn"][1]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
+                   split_k=self._splits(F, C, M, sm))
+        ops.raw_colsum(dh, self.g(L["ffn"][2]), accumulate=True)
+        dxn = self.buf("dxn", (M, C), torch.float32)
+        self._gemm(dh, self.w(L["ffn"][1]), dxn, b_major=MAJOR_MN)
+        # ---- LN2 backward + residual-gradient add + masked copy for the proj GEMMs ----
+        g1 = g_other
+        ops.raw_ln_bwd(dxn, x1, self.f(L["ln2"][0]), mean2, rstd2, g, g1, self.g(L["ln2"][0]), self.g(L["ln2"][1]),
+                       dxm=gm, dropout=self._drop(L["p"], 4 * li + 1, training))
+        # ---- proj: y = att Wp^T + bp (dropout, residual) ----
+        self._gemm(gm, att, self.g(L["proj"][0]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
+                   split_k=self._splits(C, D, M, sm))
+        ops.raw_colsum(gm, self.g(L["proj"][1]), accumulate=True)
+        datt = self.buf("datt", (M, D))
+        self._gemm(gm, self.w(L["proj"][0]), datt, b_major=MAJOR_MN)
+        # ---- attention ----
+        dqkv = self.buf("dqkv", (M, 3 * D))
+        q3, d3 = qkv.view(B, T, 3 * D), dqkv.view(B, T, 3 * D)
+        q, k, v = q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:]
+        nbytes = ops.attn_bwd_scratch_bytes(q, k, NH, H)
+        scratch = self.buf("attn_scratch", ((nbytes + 3) // 4,), torch.float32)
+        ops.raw_attn_bwd(q, k, v, att.view(B, T, D), lse, datt.view(B, T, D), d3[:, :, :D], d3[:, :, D:2 * D],
+                         d3[:, :, 2 * D:], scratch, NH, H, H ** -0.5, self._drop(L["p_attn"], 4 * li, training))
+        # ---- QKV projection ----
+        self._gemm(dqkv, xn1, self.g(L["qkv"]).view(3 * D, C), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
+                   split_k=self._splits(3 * D, C, M, sm))
+        self._gemm(dqkv, self.w(L["qkv"]).view(3 * D, C), dxn, b_major=MAJOR_MN)
+        # ---- LN1 backward + residual add (+ masked copy for the previous layer's FFN2) ----
+        g0 = g
+        ops.raw_ln_bwd(dxn, x_in, self.f(L["ln1"][0]), mean1, rstd1, g1, g0, self.g(L["ln1"][0]),
+                       self.g(L["ln1"][1]), dxm=gm if nxt is not None else None,
+                       dropout=self._drop(nxt["p"], 4 * (li - 1) + 2, training) if nxt is not None else None)
+        return g0
+
+    # ------------------------------------------------------------------ #
+    # training step
+    # ------------------------------------------------------------------ #
+    def configure_optimizer(self, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-2):
+        self._reattach()
+        self.flat.attach_grads()  # p.grad become views of the flat gradient arena
+        self.opt = FusedAdamW(self.flat, lr, betas, eps, weight_decay)
+        return self.opt
+
+    def train_step_launch(self, idx, targets, reducer=None):
+        """Enqueue forward + backward (+ bucketed DP all-reduce) + AdamW; returns the loss tensor.
+
+        Gradients are expected to be zero on entry (the fused AdamW clears them).
+        Everything is enqueued on the current stream and is CUDA-graph capturable.
+        """
+        if self.opt is None:
+            raise KernelError("call configure_optimizer() first")
+        _, loss = self.forward(idx, targets, training=True, save=True)
+        self.backward(idx, training=True, reducer=reducer)
+        if reducer is not None:
+            reducer.finish()
+        self.opt.launch(zero_grad=True)
+        ops.raw_counter_add(self.seed_dev, 1)
+        return loss
+
+    def train_step(self, idx, targets, reducer=None):
+        self.opt.upload()
+        loss = self.train_step_launch(idx, targets, reducer)
+        self.opt.t += 1
+        return loss
+
+    # ------------------------------------------------------------------ #
+    # generation: KV-cached while the window has not slid, full-window
+    # recompute afterwards (reference semantics, src/model.py:611-636)
+    # ------------------------------------------------------------------ #
+    def _decode_token(self, tok_ids, t, caches):
+        """One new token per sequence at absolute position ``t``; returns the final hidden state (B,C)."""
+        sp = self.spec
+        Bn = tok_ids.shape[0]
+        tok = self.f(sp["tok"])
+        C = tok.shape[1]
+        x = self.buf("d.x0", (Bn, C), torch.float32)
+        ops.raw_embed_fwd(tok_ids.view(Bn, 1), tok, self.f(sp["pos"]), x.view(Bn, 1, C), pos_offset=t)
+        for li, L in enumerate(sp["layers"]):
+            NH, H = L["NH"], L["H"]
+            D = NH * H
+            cache = caches[li]  # [ctx, B, 3D] time-major: row t is a contiguous (B, 3D) GEMM output
+            if L["ln1"] is not None:
+                a = self.buf("d.xn1", (Bn, C))
+                ops.raw_ln_fwd(x, self.f(L["ln1"][0]), self.f(L["ln1"][1]), a, self.buf("d.mean", (Bn,), torch.float32),
+                               self.buf("d.rstd", (Bn,), torch.float32))
+            elif x.dtype != self.at:
+                a = ops.raw_dropout_scale(x, self.buf("d.xn1", (Bn, C)))
+            else:
+                a = x
+            self._gemm(a, self.w(L["qkv"]).view(3 * D, C), cache[t])
+            q = cache[t].view(Bn, 1, 3 * D)[:, :, :D]
+            kv = cache[: t + 1].permute(1, 0, 2)  # (B, t+1, 3D) view
+            att = self.buf("d.att", (Bn, D))
+            ops.raw_attn_fwd(q, kv[:, :, D:2 * D], kv[:, :, 2 * D:], att.view(Bn, 1, D), None, NH, H, H ** -0.5)
+            if L["proj"] is not None:
+                x1 = self.buf("d.x1", (Bn, C), torch.float32)
+                self._gemm(att, self.w(L["proj"][0]), x1, bias=self.f(L["proj"][1]),
+                           residual=x if L["residual"] else None)
+            else:
+                x1 = att
+            if L["ffn"] is None:
+                x = x1
+                continue
+            if L["ln2"] is not None:
+                b = self.buf("d.xn2", (Bn, C))
+                ops.raw_ln_fwd(x1, self.f(L["ln2"][0]), self.f(L["ln2"][1]), b,
+                               self.buf("d.mean", (Bn,), torch.float32), self.buf("d.rstd", (Bn,), torch.float32))
+            elif x1.dtype != self.at:
+                b = ops.raw_dropout_scale(x1, self.buf("d.xn2", (Bn, C)))
+            else:
+                b = x1
+            out = self.buf(f"d.x2.{li & 1}", (Bn, C), torch.float32)
+            if L["ffn"][0] == "relu":
+                self._gemm(b, self.w(L["ffn"][1]), out, bias=self.f(L["ffn"][2]), relu=True)
+            else:
+                h = self.buf("d.h", (Bn, self.f(L["ffn"][1]).shape[0]))
+                self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True)
+                self._gemm(h, self.w(L["ffn"][3]), out, bias=self.f(L["ffn"][4]),
+                           residual=x1 if L["residual"] else None)
+            x = out
+        return x
+
+    @torch.no_grad()
+    def generate(self, idx, max_new_tokens, greedy=False, seed=None):
+        """(B,t0) int64 -> (B,t0+N) int64.  Sampling (softmax -> multinomial, or argmax) runs on the device."""
+        self._reattach()
+        self.flat.refresh_shadow()
+        sp = self.spec
+        Bn, t0 = idx.shape
+        total = t0 + max_new_tokens
+        seed = ops.next_seed() if seed is None else int(seed)
+        seq = torch.empty((total, Bn), device=self.device, dtype=torch.int64)  # time-major
+        seq[:t0].copy_(idx.t())
+        tok = self.f(sp["tok"])
+        V = tok.shape[0]
+        if sp["kind"] == "BigramLM":
+            logits = self.buf("d.logits", (Bn, V), torch.float32)
+            for t in range(t0 - 1, total - 1):
+                ops.raw_embed_fwd(seq[t].view(Bn, 1), tok, None, logits.view(Bn, 1, V))
+                ops.raw_sample(logits, seq[t + 1], 0, greedy, seed, t)
+            return seq.t().contiguous()
+        ctx = sp["ctx"]
+        caches = [self.buf(f"d.cache{li}", (ctx, Bn, 3 * L["NH"] * L["H"])) for li, L in enumerate(sp["layers"])]
+        logits = self.buf("d.logits", (Bn, V), torch.float32)
+        for t in range(total - 1):
+            sampling = t >= t0 - 1
+            if t < ctx:
+                x = self._decode_token(seq[t], t, caches)
+                if not sampling:
+                    continue
+                xin = x if x.dtype == self.at else ops.raw_dropout_scale(x, self.buf("d.xl", x.shape))
+                self._gemm(xin, self.w(sp["lm"][0]), logits, bias=self.f(sp["lm"][1]))
+                ops.raw_sample(logits, seq[t + 1], 0, greedy, seed, t)
+            elif sampling:
+                # window slid: absolute positions of every token change -> recompute the window
+                win = seq[t - ctx + 1: t + 1].t().contiguous()
+                full, _ = self.forward(win)
+                last = full.view(Bn, ctx, V)[:, -1, :]
+                ops.raw_sample(last, seq[t + 1], 0, greedy, seed, t)
+        return seq.t().contiguous()

@@ -1,0 +1,50 @@
+"""CUDA-graph capture of the whole training step (forward + backward + all-reduce + AdamW).
+
+Python/ctypes launch overhead (about 150 kernel launches per step) would dominate a ~2 ms step,
+so the step is recorded once and replayed.  Everything that changes per step lives in device
+memory: the token batch (static input buffers), the AdamW step counter and the dropout seed
+offset (both bumped by tiny kernels inside the graph).
+"""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, runner, batch_size, seq_len, reducer=None, warmup=2):
+        if runner.opt is None:
+            raise RuntimeError("configure_optimizer() before capturing the step")
+        self.runner = runner
+        self.reducer = reducer
+        dev = runner.device
+        self.idx = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
+        self.targets = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
+        flat, opt = runner.flat, runner.opt
+        opt.upload()
+        keep = [t.clone() for t in (flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev)]
+        keep_shadow = None if flat.shadow is None else flat.shadow.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # allocate every workspace buffer, load kernels, init NCCL channels
+                runner.train_step_launch(self.idx, self.targets, reducer)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = runner.train_step_launch(self.idx, self.targets, reducer)
+        # capture records without executing; undo the warm-up steps
+        for dst, src in zip((flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev), keep):
+            dst.copy_(src)
+        if keep_shadow is not None:
+            flat.shadow.copy_(keep_shadow)
+        flat.g.zero_()
+        flat._versions = tuple(p._version for p in flat.params.values())
+        torch.cuda.synchronize(dev)
+
+    def step(self, idx=None, targets=None):
+        """Replay one training step.  ``idx``/``targets`` may be device or pinned-host tensors."""
+        if idx is not None:
+            self.idx.copy_(idx, non_blocking=True)
+            self.targets.copy_(targets, non_blocking=True)
+        self.graph.replay()
+        self.runner.opt.t += 1
+        return self.loss

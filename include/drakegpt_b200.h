@@ -1,0 +1,221 @@
+/* drakegpt_b200 -- C-ABI of the hand-written sm_100a kernels behind the DrakeGPT
+ * training step and generation path.
+ *
+ * The reference (ChrisTho23/DrakeGPT) has no FFI layer: its hot path is a chain
+ * of PyTorch library calls.  Each entry point below replaces the group of
+ * reference call sites cited next to it (file:line under the reference repo).
+ * The host side (drakegpt_b200/*.py) binds these with ctypes and presents the
+ * reference's own nn.Module API.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in _host.  The caller owns all memory.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and
+ *     never synchronise or allocate, so every call is CUDA-graph capturable.
+ *   - return 0 on success, a negative DGPT_E* code on failure;
+ *     dgpt_last_error() returns a thread-local message for the last failure.
+ *   - row-major tensors; "ld*" are leading dimensions in ELEMENTS.
+ *   - dtype codes: DGPT_F32 = 0, DGPT_BF16 = 1.
+ *   - no CPU fallback: every compute entry fails with DGPT_E_DEVICE when the
+ *     current device is not compute capability 10.x.
+ */
+#ifndef DRAKEGPT_B200_H
+#define DRAKEGPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGPT_F32 0
+#define DGPT_BF16 1
+
+#define DGPT_OK 0
+#define DGPT_E_ARG (-1)     /* bad shape / unsupported configuration            */
+#define DGPT_E_DEVICE (-2)  /* no sm_100 device / driver entry point missing    */
+#define DGPT_E_LAUNCH (-3)  /* cudaGetLastError() after the launch was non-zero */
+
+#define DGPT_MAJOR_K 0  /* operand stored [rows, K], K contiguous                */
+#define DGPT_MAJOR_MN 1 /* operand stored [K, rows], rows contiguous (transposed) */
+
+const char* dgpt_last_error(void);
+int dgpt_abi_version(void);
+/* 0 when the current CUDA device is sm_100 and the TMA driver entry point resolves. */
+int dgpt_device_check(void);
+int dgpt_sm_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Counter-based dropout mask shared by every kernel (forward and backward
+ * regenerate it; nothing is stored):  keep(seed, site, i) =
+ *   philox4x32_10(key=seed, ctr=(i/4, site))[i%4] >= p * 2^32.
+ * Replaces nn.Dropout at src/model_component.py:324,376/401,434/454.
+ * Every entry that takes `seed` also takes `seed_dev`: an optional DEVICE
+ * uint64 added to `seed` when the kernel runs, so that a captured CUDA graph
+ * draws a fresh mask on every replay (the host bumps *seed_dev between
+ * replays).  dgpt_dropout_keep_host is a host restatement used by the tests.
+ * ------------------------------------------------------------------------- */
+int dgpt_dropout_keep_host(uint64_t seed, uint32_t site, uint64_t index, float p);
+
+/* out[i] = in[i] * keep(i) / (1-p) * (relu_aux ? relu_aux[i] > 0 : 1), cast to out_dtype
+ * (p == 0 and relu_aux == NULL: plain cast).  relu_aux is fp32; it is the ReLU backward of
+ * FeedForward (src/model_component.py:118-121). */
+int dgpt_dropout_scale(const float* in, const float* relu_aux, void* out, int out_dtype, int64_t n,
+                       float p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                       void* stream);
+/* fp32 -> bf16 copy (weight shadows for the tensor-core path). */
+int dgpt_cast_bf16(const float* in, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Embedding:  x[b,t,:] = tok[idx[b,t],:] (+ pos[t + pos_offset,:] if pos)
+ * Replaces nn.Embedding x2 + add, src/model.py:595-597 (and :95 for BigramLM,
+ * where pos == NULL and C == V).  idx is int64 like the reference's.
+ * Backward: dtok[v,:] += sum_{idx==v} dx ; dpos[t+pos_offset,:] += sum_b dx.
+ * ------------------------------------------------------------------------- */
+int dgpt_embed_fwd(const int64_t* idx, const float* tok, const float* pos, float* x, int B, int T,
+                   int C, int V, int pos_offset, void* stream);
+int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos, int B, int T,
+                   int C, int V, int pos_offset, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * LayerNorm (eps, biased variance, affine) -- nn.LayerNorm at
+ * src/model_component.py:488-489, applied at :505-506.
+ * fwd: y = (x-mean)*rstd*gamma+beta  cast to y_dtype; saves mean/rstd [M].
+ *      gamma == NULL: y = cast(x) (identity; mean/rstd untouched).
+ * bwd: dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are ACCUMULATED.
+ *      Optional fused second output for the next backward GEMM:
+ *      dxm = dx * keep(site)/(1-p) cast to dxm_dtype (dxm may be NULL).
+ * ------------------------------------------------------------------------- */
+int dgpt_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                float* mean, float* rstd, int M, int C, float eps, void* stream);
+int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                void* dxm, int dxm_dtype, float p, uint64_t seed, const uint64_t* seed_dev,
+                uint32_t site, int M, int C, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * GEMM with fused epilogue.   acc[m,n] = sum_k A(m,k) * B(n,k)
+ *   A: a_major == K  -> stored [M,K] (lda >= K);  MN -> stored [K,M] (lda >= M)
+ *   B: b_major == K  -> stored [N,K] (ldb >= K), i.e. an nn.Linear weight;
+ *      MN -> stored [K,N] (ldb >= N)
+ *   v = acc + bias[n]; relu; v *= (relu_aux[m,n] > 0); dropout(p,seed,site,
+ *   index m*N+n); v += residual[m,n]; accumulate ? D += v : D = v;
+ *   D (d_dtype) and optional D2 (d2_dtype) both receive v.
+ * Replaces nn.Linear / `@` at src/model_component.py:392-393,404 (packed QKV),
+ * :454 (proj + dropout + residual :505), :321-324 (FFN + ReLU + dropout +
+ * residual :506), src/model.py:599 (lm_head) and their autograd backward
+ * (dgrad: B MN-major; wgrad: A and B MN-major, split_k > 1 allowed).
+ *   in_dtype DGPT_F32 : exact fp32 CUDA-core kernel, any shape.
+ *   in_dtype DGPT_BF16: tcgen05/TMEM tiles fed by TMA, fp32 accumulate;
+ *                       needs K % 8 == 0 and 16-byte aligned rows.
+ * ------------------------------------------------------------------------- */
+typedef struct dgpt_gemm_args {
+  const void* A;
+  const void* B;
+  void* D;
+  void* D2;               /* optional second output                         */
+  const float* bias;      /* [N] or NULL                                    */
+  const float* residual;  /* [M, ldr] fp32 or NULL                          */
+  const void* relu_aux;   /* [M, ld_aux] (aux_dtype) or NULL                */
+  int32_t M, N, K;
+  int32_t in_dtype, d_dtype, d2_dtype, aux_dtype;
+  int32_t a_major, b_major;
+  int32_t lda, ldb, ldd, ldd2, ldr, ld_aux;
+  int32_t relu;
+  int32_t accumulate;     /* D += v (fp32 D only)                           */
+  int32_t split_k;        /* >1: partial sums combined with fp32 atomics    */
+  float dropout_p;
+  uint32_t site;
+  uint64_t seed;
+  const uint64_t* seed_dev; /* optional device-side seed offset            */
+} dgpt_gemm_args;
+int dgpt_gemm(const dgpt_gemm_args* a, void* stream);
+
+/* out[n] (+)= sum_m X[m,n]   (bias gradients) */
+int dgpt_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, int accumulate,
+                void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused causal attention over all heads.
+ *   S = scale * Q K^T ; causal mask (query i sees keys j <= i + Tk - Tq);
+ *   P = softmax(S) ; Pd = dropout(P) (no renormalisation) ; O = Pd V
+ * Replaces, per head, src/model_component.py:56-64 / :396-405 and the concat
+ * at :103/:260/:453 (head h is written at column h*H of O).
+ *   q,k,v,o: element (b, t, h, d) at  base + b*bs + t*rs + h*H + d.
+ *   lse[b,h,t] = log sum exp of the scaled, masked scores (saved for backward).
+ *   dropout index = ((b*NH+h)*Tq + i)*Tk + j.
+ *   dtype F32: exact CUDA-core kernel (any H<=128, Tk*H*8 bytes <= 200 KB).
+ *   dtype BF16: tcgen05 kernel (H == 64, Tq == Tk, Tk % 128 == 0, Tk <= 256).
+ * Backward needs `scratch` of dgpt_attn_bwd_scratch_bytes() bytes.
+ * ------------------------------------------------------------------------- */
+typedef struct dgpt_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  const void* d_o; /* backward only */
+  void* dq;
+  void* dk;
+  void* dv;
+  void* scratch;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, do_bs, do_rs;
+  int32_t dtype;
+  int32_t B, NH, H, Tq, Tk;
+  float scale;
+  float dropout_p;
+  uint32_t site;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+} dgpt_attn_args;
+int dgpt_attn_fwd(const dgpt_attn_args* a, void* stream);
+int dgpt_attn_bwd(const dgpt_attn_args* a, void* stream);
+int64_t dgpt_attn_bwd_scratch_bytes(const dgpt_attn_args* a);
+
+/* ------------------------------------------------------------------------- *
+ * Cross-entropy over the character vocabulary, mean over rows.
+ * Replaces F.cross_entropy at src/model.py:100-103,195-198,...,604-607.
+ *   loss_sum[0] += sum_m (lse_m - logits[m,target_m]) / M      (pre-zeroed)
+ *   dlogits[m,v] = (softmax(logits[m])[v] - [v==target_m]) * dloss / M
+ * dlogits may be NULL (eval).  dloss is a device scalar or NULL (= 1).
+ * ------------------------------------------------------------------------- */
+int dgpt_cross_entropy(const float* logits, int ld, const int64_t* targets, float* loss_sum,
+                       void* dlogits, int dl_dtype, int ld_dl, const float* dloss, int M, int V,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused flat AdamW (decoupled decay) over one parameter arena.
+ * Replaces optimizer.zero_grad() + AdamW.step(), src/train.py:149,151
+ * (torch.optim.AdamW defaults eps 1e-8, weight_decay 1e-2).
+ * hyper (device, 6 floats): lr, beta1, beta2, eps, weight_decay, grad_scale.
+ * step (device int64): number of updates already applied; the kernel uses
+ *   t = *step + 1 for the bias corrections and dgpt_adamw increments *step
+ *   afterwards (on the stream), so a captured CUDA graph replays correctly
+ *   without any host-side per-step state.
+ *   g' = g*grad_scale; p *= 1-lr*wd; m = lerp(m,g',1-b1); v = b2*v+(1-b2)g'^2;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * shadow (bf16, may be NULL) receives the updated weights; zero_grad != 0
+ * clears g after use.
+ * ------------------------------------------------------------------------- */
+int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n,
+               const float* hyper, int64_t* step, int zero_grad, void* stream);
+
+/* *ctr += delta on the stream (dropout seed offsets under CUDA graphs). */
+int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Next-token sampling on the device.  Replaces
+ * `logits[:, -1, :] -> F.softmax -> torch.multinomial -> torch.cat`,
+ * src/model.py:628-635.  logits: row b at logits + b*ld ([V] fp32).
+ *   greedy != 0: argmax (lowest index wins ties, like torch.argmax)
+ *   else inverse-CDF sample with u = philox(seed, step, b).
+ * Writes the token to seq[b*seq_ld + pos] (int64).
+ * ------------------------------------------------------------------------- */
+int dgpt_sample(const float* logits, int ld, int64_t* seq, int64_t seq_ld, int pos, int B, int V,
+                int greedy, uint64_t seed, uint32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAKEGPT_B200_H */

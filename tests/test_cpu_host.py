@@ -1,0 +1,127 @@
+"""CPU-only checks: library builds/loads and exports the whole C-ABI, host-side logic
+(state_dict layout, tokenizer, config, bucket planning, loud failure without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_checkpoint, load_golden
+from oracle import drake_oracle as O
+
+CFG = {"BigramLM": (80,), "SingleHeadAttentionLM": (80, 32, 8, 32), "MultiHeadAttentionLM": (80, 32, 8, 32, 4),
+       "BlocksLM": (80, 32, 8, 4, 3), "ResidualBlocksLM": (80, 32, 8, 4, 3), "TransformerLM": (80, 32, 8, 4, 3, 0.1)}
+
+
+def test_library_exports_every_declared_symbol():
+    from drakegpt_b200 import _lib, build
+    lib = build.build()
+    handle = ctypes.CDLL(lib)
+    header = open(os.path.join(ROOT, "include", "drakegpt_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dgpt_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(handle, sym), f"{sym} declared in include/drakegpt_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert handle.dgpt_abi_version() == 1
+    # host-side helper works without a GPU and is deterministic
+    handle.dgpt_dropout_keep_host.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float]
+    keeps = [handle.dgpt_dropout_keep_host(42, 1, i, 0.2) for i in range(20000)]
+    assert 0.78 < sum(keeps) / len(keeps) < 0.82
+    assert keeps == [handle.dgpt_dropout_keep_host(42, 1, i, 0.2) for i in range(20000)]
+    assert keeps != [handle.dgpt_dropout_keep_host(43, 1, i, 0.2) for i in range(20000)]
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from drakegpt_b200 import _lib
+    assert _lib.lib().dgpt_device_check() != 0
+    with pytest.raises(_lib.KernelError):
+        _lib.require_gpu()
+    from drakegpt_b200 import model as M
+    with pytest.raises(_lib.KernelError):
+        M.BigramLM(80)(torch.zeros((1, 4), dtype=torch.long))
+    with pytest.raises(_lib.KernelError):
+        M.TransformerLM(80, 32, 8, 4, 3, 0.1).generate(torch.zeros((1, 1), dtype=torch.long), 4)
+
+
+@pytest.mark.parametrize("kind", O.KINDS)
+def test_state_dict_layout_matches_reference_checkpoints(kind):
+    from drakegpt_b200 import model as M
+    sd = load_checkpoint(kind)
+    m = getattr(M, kind)(*CFG[kind])
+    fresh = m.state_dict()
+    assert list(fresh.keys()) == list(sd.keys())
+    assert all(fresh[k].shape == sd[k].shape and fresh[k].dtype == sd[k].dtype for k in sd)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    out = m.state_dict()
+    assert all(torch.equal(out[k], sd[k]) for k in sd)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == load_golden("misc_vectors.pt")["param_counts"][kind]
+    bad = dict(sd)
+    bad.pop(next(k for k in sd if k.endswith("weight")))
+    with pytest.raises(RuntimeError):
+        getattr(M, kind)(*CFG[kind]).load_state_dict(bad, strict=True)
+    if kind != "BigramLM":
+        worse = dict(sd)
+        key = next(k for k in sd if k.endswith("tril"))
+        worse[key] = torch.ones_like(sd[key])  # not causal
+        with pytest.raises(RuntimeError):
+            getattr(M, kind)(*CFG[kind]).load_state_dict(worse, strict=True)
+
+
+def test_scaled_model_shape_and_precision_choice():
+    from drakegpt_b200 import model as M
+    m = M.TransformerLM(80, 384, 256, 6, 6, 0.2)
+    assert m.precision == "bf16" and M.count_parameters(m) == 10800464 and len(m.state_dict()) == 210
+    assert M.TransformerLM(80, 32, 8, 4, 3, 0.1).precision == "fp32"
+    gold = load_golden("misc_vectors.pt")
+    P = dict(context_length=8, embedding_dim=32, num_layers=3)
+    S = dict(context_length=256, embedding_dim=384, num_layers=6)
+    for (k, s), v in gold["model_params"].items():
+        assert M.model_params(S if s else P, k, 80) == v
+    assert m.blocks[0].sa_head.heads[5].key.weight.shape == (64, 384)
+    from drakegpt_b200.model_component import Head, SingleHeadAttention
+    assert SingleHeadAttention is Head
+
+
+def test_tokenizer_config_and_batcher():
+    from drakegpt_b200 import config, preprocessing
+    gold = load_golden("misc_vectors.pt")
+    enc, dec, vs = preprocessing.get_mapper(gold["tok"]["text"])
+    assert vs == gold["tok"]["vocab_size"]
+    assert enc(gold["tok"]["probe"]) == gold["tok"]["ids"] and enc(gold["tok"]["text"]) == gold["tok"]["all_ids"]
+    assert dec(gold["tok"]["all_ids"]) == gold["tok"]["text"]
+    with pytest.raises(KeyError):
+        enc("☃")
+    torch.manual_seed(gold["get_batch"]["seed"])
+    data = torch.arange(1000, dtype=torch.long) % 80
+    x, y = preprocessing.get_batch(data, 8, 4, torch.device("cpu"))
+    assert torch.equal(x, gold["get_batch"]["x"]) and torch.equal(y, gold["get_batch"]["y"])
+    assert config.PARAMS["context_length"] == 8 and config.SCALE_PARAMS["embedding_dim"] == 384
+    assert config.TRAIN == {"iters": 10000, "eval_iters": 200, "eval_interval": 500}
+
+
+def test_gradient_bucket_plan_covers_arena():
+    from drakegpt_b200.parallel import bucket_ranges
+    slots, off = {}, 0
+    names = ["token_embedding_table.weight", "position_embedding_table.weight"]
+    names += [f"blocks.{i}.{n}" for i in range(3) for n in ("sa_head.qkv", "ffwd.net.0.weight", "ln1.weight")]
+    names += ["lm_head.weight", "lm_head.bias"]
+    for n in names:
+        k = 100 + len(n)
+        slots[n] = (off, k, (k,))
+        off += (k + 63) // 64 * 64
+    n_live = off
+    slots["ln_f.weight"] = (off, 32, (32,))
+    groups = [("lm_head.",)] + [(f"blocks.{i}.",) for i in (2, 1, 0)] + [("token_embedding_table.", "position_embedding_table.")]
+    rng = bucket_ranges(slots, n_live, groups)
+    assert len(rng) == 5
+    covered = sorted(rng)
+    assert covered[0][0] == 0 and covered[-1][1] == n_live
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    with pytest.raises(ValueError):
+        bucket_ranges(slots, n_live, groups[:-1])
