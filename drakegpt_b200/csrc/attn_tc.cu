@@ -1,15 +1,517 @@
-// Tensor-mode fused causal attention (tcgen05 / TMEM / TMA).  Placeholder until the
-// kernel lands: bf16 attention is served by the CUDA-core kernel in attn_simt.cu.
+// Tensor-mode fused causal attention for sm_100a (head size 64, T in {128, 256}).
+//
+// Forward  (one CTA per (batch, head, 128-query tile), two CTAs resident per SM):
+//   TMA loads Q, K, V tiles (128B swizzle) -> tcgen05.mma S = Q K^T into TMEM (the whole
+//   128 x T score row block fits: no online rescaling) -> 128 softmax threads, one per
+//   query row, read S with tcgen05.ld, apply the causal mask, exp2, Philox dropout, and
+//   write bf16 P straight into the swizzled K-major shared-memory layout the next MMA
+//   reads -> tcgen05.mma O = P V (V consumed MN-major from its row-major tile) -> the same
+//   threads scale by 1/rowsum and store bf16 O at column h*64 (the head concat is free).
+//   The T x T probabilities never touch HBM; only the log-sum-exp per row is saved.
+//
+// Backward (one CTA per (batch, head)): recomputes S^T = K Q^T and dP^T = V dO^T per
+//   (query tile, key tile) pair on the tensor cores, 256 threads turn them into
+//   Pd^T / dS^T (same Philox mask as forward) in shared memory, and three more MMAs
+//   accumulate dV += Pd^T dO, dK += dS^T Q, dQ += dS K in TMEM.  Every operand view
+//   (K-major or MN-major) is a descriptor over the same TMA-loaded row-major tiles.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dgpt {
-bool attn_tc_supported(const dgpt_attn_args*) { return false; }
-int launch_attn_fwd_tc(const dgpt_attn_args*, cudaStream_t) {
-  set_error("attn_fwd(tensor): not available");
-  return DGPT_E_ARG;
+
+using namespace ptx;
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_outer);
+
+static constexpr int HD = 64;     // head size
+static constexpr int QT = 128;    // query / key tile rows
+static constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnTcP {
+  void *o, *dq, *dk, *dv;
+  const void *o_in, *d_o;
+  float* lse;
+  int64_t o_rs, dq_rs, dk_rs, dv_rs, do_rs;
+  int B, NH, T;
+  float scale, inv_keep;
+  uint32_t thr, site;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
-int launch_attn_bwd_tc(const dgpt_attn_args*, cudaStream_t) {
-  set_error("attn_bwd(tensor): not available");
-  return DGPT_E_ARG;
+
+// write 32 consecutive bf16 (cols [c0, c0+32) of `row`) of a [128 x 64*n] K-major SW128 tile set
+__device__ __forceinline__ void store_row32_sw128(uint8_t* tile_base, int row, int c0, const float (&v)[32]) {
+  uint8_t* blk = tile_base + (c0 >> 6) * 16384 + row * 128;
+  const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 w;
+    w.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+    w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+    w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+    w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(blk + (((chunk0 + j) ^ (row & 7)) << 4)) = w;
+  }
 }
+
+// ===========================================================================
+// forward
+// ===========================================================================
+static constexpr int kFwdThreads = 192;
+static constexpr int kFwdSmem = 64 * 1024 + 32 * 1024 + 1024 + 128;
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, AttnTcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                 // 16 KB        | P k-blocks 0..3 (4 x 16 KB) overlay Q and K
+  uint8_t* sK = smem + 16384;         // 2 x 16 KB    | once S has been computed
+  uint8_t* sP = smem;
+  uint8_t* sV = smem + 65536;         // 4 x 8 KB (64 kv rows each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint64_t *qk_full = bars, *v_full = bars + 1, *s_full = bars + 2, *p_full = bars + 3, *o_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = p.T / QT;
+  const int qt = ntile - 1 - (int)blockIdx.x;  // heavier tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nkv = qt + 1;                      // key tiles this query tile can see
+  const int row0 = b * p.T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qk_full, 16384 * (1 + nkv));
+      tma_load_2d(sQ, &map_q, qk_full, h * HD, row0 + qt * QT);
+      for (int j = 0; j < nkv; ++j) tma_load_2d(sK + j * 16384, &map_k, qk_full, h * HD, row0 + j * QT);
+      mbar_expect_tx(v_full, 8192 * 2 * nkv);
+      for (int kb = 0; kb < 2 * nkv; ++kb) tma_load_2d(sV + kb * 8192, &map_v, v_full, h * HD, row0 + kb * 64);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(qk_full, 0);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+      for (int j = 0; j < nkv; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem + j * 128, make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                      make_smem_desc_sw128(ak + j * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+      }
+      tc_commit(s_full);
+      mbar_wait(v_full, 0);
+      mbar_wait(p_full, 0);
+      tc_fence_after();
+      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+      for (int kb = 0; kb < 2 * nkv; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem, make_smem_desc_sw128(ap + kb * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(av + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) > 0);
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    // ---------------------------- softmax + epilogue: one thread per query row ----------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int qg = qt * QT + row;  // query position inside the sequence
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
+    const int ncols = nkv * QT;
+    uint64_t seed = p.seed;
+    if (p.thr && p.seed_dev) seed += *p.seed_dev;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    // tcgen05.ld is warp-collective: loop bounds must be warp-uniform, so use the LAST row of this
+    // warp to decide which 32-column chunks are fully masked
+    const int qg_max = qt * QT + quad * 32 + 31;
+    float mx = -INFINITY;
+    for (int c = 0; c < ncols && c <= qg_max; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c + j <= qg) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float sc = p.scale * kLog2e;
+    const float msc = mx * sc;
+    float sum = 0.f;
+    const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qg) * (uint64_t)p.T;
+    for (int c = 0; c < ncols; c += 32) {
+      float e[32];
+      if (c > qg_max) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = 0.f;
+      } else {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = (c + j <= qg) ? exp2f(__uint_as_float(r[j]) * sc - msc) : 0.f;
+          sum += v;
+          e[j] = v;
+        }
+        if (p.thr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const u32x4 bits = dropout_bits4(seed, p.site, (base + c + 4 * j) >> 2);
+            if (bits.x < p.thr) e[4 * j] = 0.f;
+            if (bits.y < p.thr) e[4 * j + 1] = 0.f;
+            if (bits.z < p.thr) e[4 * j + 2] = 0.f;
+            if (bits.w < p.thr) e[4 * j + 3] = 0.f;
+          }
+        }
+      }
+      store_row32_sw128(sP, row, c, e);
+    }
+    if (p.lse) p.lse[((int64_t)b * p.NH + h) * p.T + qg] = mx * p.scale + logf(sum);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_full);
+    // epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float oscale = p.inv_keep / sum;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.o) + (int64_t)(row0 + qg) * p.o_rs + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(r[8 * j]) * oscale, __uint_as_float(r[8 * j + 1]) * oscale);
+        w.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * oscale, __uint_as_float(r[8 * j + 3]) * oscale);
+        w.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * oscale, __uint_as_float(r[8 * j + 5]) * oscale);
+        w.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * oscale, __uint_as_float(r[8 * j + 7]) * oscale);
+        *reinterpret_cast<uint4*>(orow + c + 8 * j) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ===========================================================================
+// backward
+// ===========================================================================
+static constexpr int kBwdThreads = 64 + 256;
+static constexpr int kBwdSmem = 8 * 16384 + 2 * 32768 + 2048 + 1024 + 128;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do, AttnTcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                  // [2][128 x 64]
+  uint8_t* sK = smem + 2 * 16384;
+  uint8_t* sV = smem + 4 * 16384;
+  uint8_t* sG = smem + 6 * 16384;      // dO
+  uint8_t* sPd = smem + 8 * 16384;     // Pd^T  [128 kv x 128 q] as two K-major k-blocks
+  uint8_t* sDs = sPd + 32768;          // dS^T
+  float* lse_s = reinterpret_cast<float*>(sDs + 32768);  // [256]  lse * log2(e)
+  float* D_s = lse_s + 256;                              // [256]  rowsum(dO * O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(D_s + 256);
+  uint64_t *ld_full = bars, *st_full = bars + 1, *ps_full = bars + 2, *drained = bars + 3, *acc_done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ntile = p.T / QT;
+  const int npair = ntile == 1 ? 1 : 3;  // (0,0) | (0,0),(1,0),(1,1)
+  const int row0 = b * p.T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    prefetch_tensormap(&map_do);
+    mbar_init(ld_full, 1);
+    mbar_init(st_full, 1);
+    mbar_init(ps_full, 8);
+    mbar_init(drained, 8);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(ld_full, 16384 * 4 * ntile);
+      for (int t = 0; t < ntile; ++t) {
+        tma_load_2d(sQ + t * 16384, &map_q, ld_full, h * HD, row0 + t * QT);
+        tma_load_2d(sK + t * 16384, &map_k, ld_full, h * HD, row0 + t * QT);
+        tma_load_2d(sV + t * 16384, &map_v, ld_full, h * HD, row0 + t * QT);
+        tma_load_2d(sG + t * 16384, &map_do, ld_full, h * HD, row0 + t * QT);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T
+      constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dV, dK
+      constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dQ
+      mbar_wait(ld_full, 0);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG);
+      const uint32_t aPd = smem_u32(sPd), aDs = smem_u32(sDs);
+      for (int pr = 0; pr < npair; ++pr) {
+        const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+        const uint32_t ph = pr & 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem + TM_ST, make_smem_desc_sw128(aK + j * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aQ + i * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem + TM_DP, make_smem_desc_sw128(aV + j * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aG + i * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+        tc_commit(st_full);
+        mbar_wait(ps_full, ph);
+        if (pr > 0) mbar_wait(drained, (pr - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc_vk = (pr == 1) ? 1u : 0u;  // second pair of key tile 0 accumulates
+        const uint32_t acc_q = (pr == 2) ? 1u : 0u;   // second pair of query tile 1 accumulates
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a_k = (k >> 2) * 16384 + (k & 3) * 32;  // K-major A over the q dimension
+          tc_mma_bf16(tmem + TM_DV, make_smem_desc_sw128(aPd + a_k, 16, 1024),
+                      make_smem_desc_sw128(aG + i * 16384 + k * 2048, 8192, 1024), id_kmn, acc_vk | (k > 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a_k = (k >> 2) * 16384 + (k & 3) * 32;
+          tc_mma_bf16(tmem + TM_DK, make_smem_desc_sw128(aDs + a_k, 16, 1024),
+                      make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024), id_kmn, acc_vk | (k > 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // A = dS (q x kv) read MN-major out of the dS^T tile
+          tc_mma_bf16(tmem + TM_DQ, make_smem_desc_sw128(aDs + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_q | (k > 0));
+        if (pr == npair - 1) tc_commit(acc_done);
+      }
+    }
+  } else {
+    // ------------------------------ 256 compute threads --------------------------------
+    const int cw = warp - 2;            // 0..7
+    const int quad = warp & 3;          // TMEM lane quadrant of this warp
+    const int half = cw >> 2;           // which 64 of the 128 q columns
+    const int kvl = quad * 32 + lane;   // key row inside the tile
+    const int ct = threadIdx.x - 64;    // 0..255
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    uint64_t seed = p.seed;
+    if (p.thr && p.seed_dev) seed += *p.seed_dev;
+    // D_i = dO_i . O_i and lse_i * log2e for every query row of this (b, h)
+    if (ct < p.T) {
+      const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (int64_t)(row0 + ct) * p.do_rs + h * HD);
+      const uint4* op = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o_in) + (int64_t)(row0 + ct) * p.o_rs + h * HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 g = __ldg(gp + c), o = __ldg(op + c);
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[t]));
+          const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
+          acc = fmaf(gf.x, of.x, acc);
+          acc = fmaf(gf.y, of.y, acc);
+        }
+      }
+      D_s[ct] = acc;
+      lse_s[ct] = p.lse[((int64_t)b * p.NH + h) * p.T + ct] * kLog2e;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float sc = p.scale * kLog2e;
+
+    auto drain = [&](uint32_t tm_col, void* dst, int64_t rs, int tile) {
+      // 128 x 64 fp32 accumulator -> bf16 rows; this thread owns 32 columns of one row
+      uint32_t r[32];
+      tmem_ld32(lane_addr + tm_col + half * 32, r);
+      tmem_ld_wait();
+      __nv_bfloat16* rowp = reinterpret_cast<__nv_bfloat16*>(dst) + (int64_t)(row0 + tile * QT + kvl) * rs + h * HD + half * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+        w.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+        w.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+        w.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+        *reinterpret_cast<uint4*>(rowp + 8 * j) = w;
+      }
+    };
+
+    for (int pr = 0; pr < npair; ++pr) {
+      const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+      mbar_wait(st_full, pr & 1);  // also implies the accumulate MMAs of the previous pair retired
+      tc_fence_after();
+      if (pr == 1) {               // (0,0) finished query tile 0
+        drain(TM_DQ, p.dq, p.dq_rs, 0);
+      } else if (pr == 2) {        // (1,0) finished key tile 0
+        drain(TM_DV, p.dv, p.dv_rs, 0);
+        drain(TM_DK, p.dk, p.dk_rs, 0);
+      }
+      if (pr > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(drained);
+      }
+      const bool diag = (i == j);
+      const int kvg = j * QT + kvl;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        const int q0 = half * 64 + c;  // first q column (inside the tile) of this chunk
+        uint32_t st[32], dp[32];
+        tmem_ld32(lane_addr + TM_ST + q0, st);
+        tmem_ld32(lane_addr + TM_DP + q0, dp);
+        tmem_ld_wait();
+        float pd[32], ds[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int ql = q0 + t;
+          const int qi = i * QT + ql;
+          const bool valid = !diag || kvl <= ql;
+          const float pv = valid ? exp2f(__uint_as_float(st[t]) * sc - lse_s[qi]) : 0.f;
+          bool keep = true;
+          if (p.thr) {
+            const uint64_t idx = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + kvg;
+            keep = dropout_keep(seed, p.site, idx, p.thr);
+          }
+          const float pdv = keep ? pv * p.inv_keep : 0.f;
+          const float dpv = keep ? __uint_as_float(dp[t]) * p.inv_keep : 0.f;
+          pd[t] = pdv;
+          ds[t] = pv * (dpv - D_s[qi]) * p.scale;
+        }
+        store_row32_sw128(sPd, kvl, q0, pd);
+        store_row32_sw128(sDs, kvl, q0, ds);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ps_full);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int last = ntile - 1;
+    drain(TM_DV, p.dv, p.dv_rs, last);
+    drain(TM_DK, p.dk, p.dk_rs, last);
+    drain(TM_DQ, p.dq, p.dq_rs, last);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ===========================================================================
+// host
+// ===========================================================================
+bool attn_tc_supported(const dgpt_attn_args* a) {
+  if (a->dtype != DGPT_BF16 || a->H != HD || a->Tq != a->Tk) return false;
+  if (a->Tk != 128 && a->Tk != 256) return false;
+  const int64_t T = a->Tk;
+  auto ok = [&](const void* ptr, int64_t bs, int64_t rs) {
+    return ptr && ((uintptr_t)ptr & 15) == 0 && rs % 8 == 0 && bs == T * rs;
+  };
+  if (!ok(a->q, a->q_bs, a->q_rs) || !ok(a->k, a->k_bs, a->k_rs) || !ok(a->v, a->v_bs, a->v_rs) ||
+      !ok(a->o, a->o_bs, a->o_rs))
+    return false;
+  if (a->d_o) {  // backward call
+    if (!ok(a->d_o, a->do_bs, a->do_rs) || !ok(a->dq, a->dq_bs, a->dq_rs) || !ok(a->dk, a->dk_bs, a->dk_rs) ||
+        !ok(a->dv, a->dv_bs, a->dv_rs) || !a->lse)
+      return false;
+  }
+  return true;
+}
+
+static AttnTcP make_tc_params(const dgpt_attn_args* a) {
+  AttnTcP p;
+  p.o = a->o; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv; p.o_in = a->o; p.d_o = a->d_o; p.lse = a->lse;
+  p.o_rs = a->o_rs; p.dq_rs = a->dq_rs; p.dk_rs = a->dk_rs; p.dv_rs = a->dv_rs; p.do_rs = a->do_rs;
+  p.B = a->B; p.NH = a->NH; p.T = a->Tk;
+  p.scale = a->scale; p.inv_keep = 1.f / (1.f - a->dropout_p);
+  p.thr = dropout_threshold(a->dropout_p); p.site = a->site; p.seed = a->seed; p.seed_dev = a->seed_dev;
+  return p;
+}
+
+int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  const int64_t rows = (int64_t)a->B * a->Tk, cols = (int64_t)a->NH * HD;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&mq, a->q, cols, rows, a->q_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mk, a->k, cols, rows, a->k_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mv, a->v, cols, rows, a->v_rs, 64))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    if (e != cudaSuccess) { set_error("attn_fwd_tc: smem attribute: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
+    attr = true;
+  }
+  AttnTcP p = make_tc_params(a);
+  dim3 grid(a->Tk / QT, a->NH, a->B);
+  attn_fwd_tc_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, p);
+  return check_launch("attn_fwd_tc");
+}
+
+int launch_attn_bwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
+  CUtensorMap mq, mk, mv, mg;
+  const int64_t rows = (int64_t)a->B * a->Tk, cols = (int64_t)a->NH * HD;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&mq, a->q, cols, rows, a->q_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mk, a->k, cols, rows, a->k_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mv, a->v, cols, rows, a->v_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mg, a->d_o, cols, rows, a->do_rs, QT))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) { set_error("attn_bwd_tc: smem attribute: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
+    attr = true;
+  }
+  AttnTcP p = make_tc_params(a);
+  dim3 grid(a->NH, a->B);
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, p);
+  return check_launch("attn_bwd_tc");
+}
+
 }  // namespace dgpt

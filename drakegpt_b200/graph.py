@@ -20,7 +20,6 @@ class GraphedTrainStep:
         flat, opt = runner.flat, runner.opt
         opt.upload()
         keep = [t.clone() for t in (flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev)]
-        keep_shadow = None if flat.shadow is None else flat.shadow.clone()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -34,10 +33,8 @@ class GraphedTrainStep:
         # capture records without executing; undo the warm-up steps
         for dst, src in zip((flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev), keep):
             dst.copy_(src)
-        if keep_shadow is not None:
-            flat.shadow.copy_(keep_shadow)
         flat.g.zero_()
-        flat._versions = tuple(p._version for p in flat.params.values())
+        flat.refresh_shadow(force=True)  # bf16 shadows follow the restored fp32 masters
         torch.cuda.synchronize(dev)
 
     def step(self, idx=None, targets=None):

@@ -134,26 +134,28 @@ def state_dict_schema(kind, vocab_size, embedding_dim=32, context_length=8,
 def synthetic_state_dict(kind, seed, **cfg):
     """Deterministic weights from a formula both sides can regenerate.
 
-    Not the reference's init (that is torch-constructor-order dependent); used
-    for large shapes whose weights cannot be shipped as fixtures.  Linear/
-    embedding weights ~ N(0, 0.02^2)*k, LayerNorm ~ 1 + small, biases small.
+    Same distributions as the reference's constructors draw (nn.Linear: weight and
+    bias ~ U(+-1/sqrt(fan_in)); nn.Embedding ~ N(0,1); nn.LayerNorm 1/0, here with a
+    small perturbation so the affine part is exercised), but generated key by key
+    from one seeded generator instead of in torch-constructor order.  Used for
+    shapes whose weights cannot be shipped as fixtures (TransformerLM_scaled).
     """
     g = torch.Generator().manual_seed(seed)
     sd = OrderedDict()
     T = cfg.get("context_length", 8)
-    for key, shape in state_dict_schema(kind, **cfg).items():
+    schema = state_dict_schema(kind, **cfg)
+    for key, shape in schema.items():
         if key.endswith("tril"):
             sd[key] = torch.tril(torch.ones(T, T))
         elif ".ln" in key or key.startswith("ln_f"):
             base = 1.0 if key.endswith("weight") else 0.0
-            sd[key] = base + 0.1 * torch.randn(shape, generator=g)
-        elif key.endswith("bias"):
-            sd[key] = 0.02 * torch.randn(shape, generator=g)
+            sd[key] = base + 0.05 * torch.randn(shape, generator=g)
         elif "embedding" in key:
-            sd[key] = 0.5 * torch.randn(shape, generator=g)
+            sd[key] = torch.randn(shape, generator=g)
         else:
-            fan_in = shape[1]
-            sd[key] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+            fan_in = shape[1] if len(shape) == 2 else schema[key[:-4] + "weight"][1]
+            bound = 1.0 / math.sqrt(fan_in)
+            sd[key] = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
     return sd
 
 

@@ -217,6 +217,39 @@ def test_attention_dropout_matches_host_mask():
         torch.testing.assert_close(got.cpu(), want.transpose(1, 2).reshape(B, T, NH * H), rtol=1e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("T", [128, 256])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_attention_tcgen05_vs_exact(T, p):
+    """bf16 tcgen05 attention (fwd + bwd) == exact fp32 kernel on the same bf16-rounded q,k,v,dO and mask."""
+    g = torch.Generator().manual_seed(T + int(p * 10))
+    B, NH, H = 2, 3, 64
+    D = NH * H
+    qkv = (torch.randn(B, T, 3 * D, generator=g) * 0.8).bfloat16()
+    go = torch.randn(B, T, D, generator=g).bfloat16()
+    drop = ops.Dropout(p, 31337, 6) if p > 0 else None
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        x = qkv.to(DEV).to(dt)
+        q, k, v = x[:, :, :D], x[:, :, D:2 * D], x[:, :, 2 * D:]
+        o = torch.empty(B, T, D, device=DEV, dtype=dt)
+        lse = torch.empty(B, NH, T, device=DEV)
+        ops.raw_attn_fwd(q, k, v, o, lse, NH, H, H ** -0.5, drop)
+        dx = torch.full((B, T, 3 * D), float("nan"), device=DEV, dtype=dt)
+        scratch = torch.empty((ops.attn_bwd_scratch_bytes(q, k, NH, H) + 3) // 4, device=DEV)
+        ops.raw_attn_bwd(q, k, v, o, lse, go.to(DEV).to(dt), dx[:, :, :D], dx[:, :, D:2 * D], dx[:, :, 2 * D:], scratch,
+                         NH, H, H ** -0.5, drop)
+        res[dt] = (o.float().cpu(), lse.cpu(), dx.float().cpu())
+    (o32, l32, d32), (o16, l16, d16) = res[torch.float32], res[torch.bfloat16]
+    torch.testing.assert_close(l16, l32, rtol=1e-3, atol=2e-3)
+    assert (o16 - o32).abs().max() <= 3e-2, (o16 - o32).abs().max()
+    assert ((o16 - o32).norm() / o32.norm()) <= 1e-2
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        a, b_ = d16[:, :, sl], d32[:, :, sl]
+        assert torch.isfinite(a).all(), name
+        rel = ((a - b_).norm() / b_.norm()).item()
+        assert rel <= 2e-2, (name, rel)
+
+
 def test_fused_adamw_matches_oracle_and_skips_frozen():
     from drakegpt_b200.optim import FlatParams, FusedAdamW
     torch.manual_seed(0)
