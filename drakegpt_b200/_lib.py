@@ -72,7 +72,7 @@ def _declare(lib):
         "dgpt_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dgpt_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dgpt_ln_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, f32, vp],
-        "dgpt_ln_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, u64, vp, u32, i32, i32, vp],
+        "dgpt_ln_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, f32, u64, vp, u32, i32, i32, vp],
         "dgpt_gemm": [C.POINTER(GemmArgs), vp],
         "dgpt_colsum": [vp, i32, i32, i32, i32, vp, i32, vp],
         "dgpt_attn_fwd": [C.POINTER(AttnArgs), vp],

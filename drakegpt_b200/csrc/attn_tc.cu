@@ -9,11 +9,11 @@
 //   threads scale by 1/rowsum and store bf16 O at column h*64 (the head concat is free).
 //   The T x T probabilities never touch HBM; only the log-sum-exp per row is saved.
 //
-// Backward (one CTA per (batch, head)): recomputes S^T = K Q^T and dP^T = V dO^T per
-//   (query tile, key tile) pair on the tensor cores, 256 threads turn them into
-//   Pd^T / dS^T (same Philox mask as forward) in shared memory, and three more MMAs
-//   accumulate dV += Pd^T dO, dK += dS^T Q, dQ += dS K in TMEM.  Every operand view
-//   (K-major or MN-major) is a descriptor over the same TMA-loaded row-major tiles.
+// Backward (one CTA per (batch, head)): recomputes S = Q K^T and dP = dO V^T per
+//   (query tile, key tile) pair on the tensor cores, 256 threads (two per query row) turn
+//   them into Pd / dS (same counter-based mask as forward) in shared memory, and three more
+//   MMAs accumulate dV += Pd^T dO, dK += dS^T Q, dQ += dS K in TMEM.  Every operand view
+//   (K-major or MN-major, transposed or not) is a descriptor over the same row-major tiles.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -242,8 +242,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* sK = smem + 2 * 16384;
   uint8_t* sV = smem + 4 * 16384;
   uint8_t* sG = smem + 6 * 16384;      // dO
-  uint8_t* sPd = smem + 8 * 16384;     // Pd^T  [128 kv x 128 q] as two K-major k-blocks
-  uint8_t* sDs = sPd + 32768;          // dS^T
+  uint8_t* sPd = smem + 8 * 16384;     // Pd  [128 q x 128 kv] as two K-major 64-key blocks
+  uint8_t* sDs = sPd + 32768;          // dS  (same layout)
   float* lse_s = reinterpret_cast<float*>(sDs + 32768);  // [256]  lse * log2(e)
   float* D_s = lse_s + 256;                              // [256]  rowsum(dO * O)
   uint64_t* bars = reinterpret_cast<uint64_t*>(D_s + 256);
@@ -287,9 +287,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T
-      constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dV, dK
-      constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dQ
+      constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP
+      constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dQ
+      constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dV, dK
       mbar_wait(ld_full, 0);
       tc_fence_after();
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG);
@@ -297,36 +297,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int pr = 0; pr < npair; ++pr) {
         const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
         const uint32_t ph = pr & 1;
+        // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal
+        // test and the dropout quads (which run along the key axis) are per-thread like in forward
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + TM_ST, make_smem_desc_sw128(aK + j * 16384 + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aQ + i * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+          tc_mma_bf16(tmem + TM_ST, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aK + j * 16384 + k * 32, 16, 1024), id_kk, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + TM_DP, make_smem_desc_sw128(aV + j * 16384 + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aG + i * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+          tc_mma_bf16(tmem + TM_DP, make_smem_desc_sw128(aG + i * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aV + j * 16384 + k * 32, 16, 1024), id_kk, k > 0);
         tc_commit(st_full);
         mbar_wait(ps_full, ph);
         if (pr > 0) mbar_wait(drained, (pr - 1) & 1);
         tc_fence_after();
         const uint32_t acc_vk = (pr == 1) ? 1u : 0u;  // second pair of key tile 0 accumulates
         const uint32_t acc_q = (pr == 2) ? 1u : 0u;   // second pair of query tile 1 accumulates
+        // dV_j += Pd^T dO_i, dK_j += dS^T Q_i: A = the [q x kv] tile read MN-major (M = kv: 64-wide
+        // chunks 16 KB apart, K = q rows); B = dO_i / Q_i read MN-major (N = d, K = q rows)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t a_k = (k >> 2) * 16384 + (k & 3) * 32;  // K-major A over the q dimension
-          tc_mma_bf16(tmem + TM_DV, make_smem_desc_sw128(aPd + a_k, 16, 1024),
-                      make_smem_desc_sw128(aG + i * 16384 + k * 2048, 8192, 1024), id_kmn, acc_vk | (k > 0));
-        }
+        for (int k = 0; k < 8; ++k)
+          tc_mma_bf16(tmem + TM_DV, make_smem_desc_sw128(aPd + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(aG + i * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_vk | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          tc_mma_bf16(tmem + TM_DK, make_smem_desc_sw128(aDs + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_vk | (k > 0));
+        // dQ_i += dS K_j: A = dS K-major over kv (two 64-wide k-blocks), B = K_j MN-major (N = d, K = kv rows)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t a_k = (k >> 2) * 16384 + (k & 3) * 32;
-          tc_mma_bf16(tmem + TM_DK, make_smem_desc_sw128(aDs + a_k, 16, 1024),
-                      make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024), id_kmn, acc_vk | (k > 0));
+          tc_mma_bf16(tmem + TM_DQ, make_smem_desc_sw128(aDs + a_k, 16, 1024),
+                      make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_kmn, acc_q | (k > 0));
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // A = dS (q x kv) read MN-major out of the dS^T tile
-          tc_mma_bf16(tmem + TM_DQ, make_smem_desc_sw128(aDs + k * 2048, 16384, 1024),
-                      make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_q | (k > 0));
         if (pr == npair - 1) tc_commit(acc_done);
       }
     }
@@ -334,8 +337,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // ------------------------------ 256 compute threads --------------------------------
     const int cw = warp - 2;            // 0..7
     const int quad = warp & 3;          // TMEM lane quadrant of this warp
-    const int half = cw >> 2;           // which 64 of the 128 q columns
-    const int kvl = quad * 32 + lane;   // key row inside the tile
+    const int half = cw >> 2;           // which 64 of the 128 key columns
+    const int kvl = quad * 32 + lane;   // accumulator row inside the tile (query row for S/dP/dQ, key row for dV/dK)
     const int ct = threadIdx.x - 64;    // 0..255
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint64_t seed = p.seed;
@@ -396,33 +399,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (lane == 0) mbar_arrive(drained);
       }
       const bool diag = (i == j);
-      const int kvg = j * QT + kvl;
+      const int qi = i * QT + kvl;  // this thread's query row (kvl = row inside the tile)
+      const float lse2 = lse_s[qi], Dq = D_s[qi];
+      const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + (uint64_t)(j * QT);
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
-        const int q0 = half * 64 + c;  // first q column (inside the tile) of this chunk
+        const int k0 = half * 64 + c;  // first key column (inside the tile) of this chunk
         uint32_t st[32], dp[32];
-        tmem_ld32(lane_addr + TM_ST + q0, st);
-        tmem_ld32(lane_addr + TM_DP + q0, dp);
+        tmem_ld32(lane_addr + TM_ST + k0, st);
+        tmem_ld32(lane_addr + TM_DP + k0, dp);
         tmem_ld_wait();
         float pd[32], ds[32];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int ql = q0 + t;
-          const int qi = i * QT + ql;
-          const bool valid = !diag || kvl <= ql;
-          const float pv = valid ? exp2f(__uint_as_float(st[t]) * sc - lse_s[qi]) : 0.f;
-          bool keep = true;
-          if (p.thr) {
-            const uint64_t idx = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + kvg;
-            keep = dropout_keep(seed, p.site, idx, p.thr);
+        for (int t4 = 0; t4 < 8; ++t4) {
+          u32x4 bits = u32x4{0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+          if (p.thr) bits = dropout_bits4(seed, p.site, (base + k0 + 4 * t4) >> 2);
+          const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int t = 4 * t4 + u;
+            const bool valid = !diag || (k0 + t) <= kvl;
+            const float pv = valid ? exp2f(__uint_as_float(st[t]) * sc - lse2) : 0.f;
+            const bool keep = bw[u] >= p.thr;
+            const float dpv = keep ? __uint_as_float(dp[t]) * p.inv_keep : 0.f;
+            pd[t] = keep ? pv * p.inv_keep : 0.f;
+            ds[t] = pv * (dpv - Dq) * p.scale;
           }
-          const float pdv = keep ? pv * p.inv_keep : 0.f;
-          const float dpv = keep ? __uint_as_float(dp[t]) * p.inv_keep : 0.f;
-          pd[t] = pdv;
-          ds[t] = pv * (dpv - D_s[qi]) * p.scale;
         }
-        store_row32_sw128(sPd, kvl, q0, pd);
-        store_row32_sw128(sDs, kvl, q0, ds);
+        store_row32_sw128(sPd, kvl, k0, pd);
+        store_row32_sw128(sDs, kvl, k0, ds);
       }
       fence_proxy_async();
       tc_fence_before();

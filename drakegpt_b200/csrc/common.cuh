@@ -58,17 +58,30 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1
   return u32x4{c0, c1, c2, c3};
 }
 
-// four consecutive elements [4*q, 4*q+3] of a dropout site share one Philox call
+// ---------------------------------------------------------------------------
+// Dropout mask: counter-based SplitMix64.  Four consecutive elements [4q, 4q+3] of a
+// dropout site share ONE 64-bit hash (16 bits each), i.e. ~5 integer instructions per
+// element instead of ~25 with Philox4x32-10 -- the mask is regenerated inside the
+// attention and GEMM-epilogue inner loops, so its cost is on the critical path.
+//   state(q) = seed + q * golden + (site+1) * K   (the SplitMix64 stream, offset per site)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
 __host__ __device__ __forceinline__ u32x4 dropout_bits4(uint64_t seed, uint32_t site, uint64_t quad) {
-  return philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), site, 0x44524b45u /* "DRKE" */,
-                       (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t h = mix64(seed + quad * 0x9E3779B97F4A7C15ull + (uint64_t)(site + 1u) * 0xD1B54A32D192ED03ull);
+  return u32x4{(uint32_t)(h & 0xFFFFu), (uint32_t)((h >> 16) & 0xFFFFu), (uint32_t)((h >> 32) & 0xFFFFu),
+               (uint32_t)(h >> 48)};
 }
 
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-  // keep iff bits >= threshold; P(drop) = threshold / 2^32
-  double t = (double)p * 4294967296.0;
+  // keep iff 16-bit lane >= threshold; P(drop) = threshold / 65536 (0 = dropout off)
+  double t = (double)p * 65536.0 + 0.5;
   if (t < 0.0) t = 0.0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
 }
 

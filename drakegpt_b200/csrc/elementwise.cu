@@ -72,19 +72,20 @@ __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __rest
   dpos[(int64_t)pos_offset * C + i] += acc;
 }
 
-// dtok[v, c0:c0+128] += sum_{m: idx[m]==v} dx[m, c]; one CTA per (v, column chunk).
-// The 80-row table would serialise global atomics, so each CTA scans idx, builds
-// an ordered list of matching rows in shared memory and reduces them itself.
-__global__ void __launch_bounds__(128) embed_bwd_tok_kernel(const int64_t* __restrict__ idx,
+// dtok[v, :] += sum_{m: idx[m]==v} dx[m, :]; one CTA per (v, 512-column chunk).
+// The 80-row table would serialise global atomics, so each CTA scans idx (256 entries per
+// step), builds an ORDERED list of matching rows in shared memory (deterministic sum order)
+// and reduces them itself, two columns per thread.
+__global__ void __launch_bounds__(256) embed_bwd_tok_kernel(const int64_t* __restrict__ idx,
                                                             const float* __restrict__ dx,
                                                             float* __restrict__ dtok, int M, int C) {
-  __shared__ int list[128];
-  __shared__ int warp_cnt[4];
+  __shared__ int list[256];
+  __shared__ int warp_cnt[8];
   const int v = blockIdx.x;
-  const int c = blockIdx.y * 128 + threadIdx.x;
+  const int c0 = blockIdx.y * 512 + threadIdx.x, c1 = c0 + 256;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float acc = 0.f;
-  for (int base = 0; base < M; base += 128) {
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int base = 0; base < M; base += 256) {
     const int m = base + threadIdx.x;
     const bool hit = (m < M) && (idx[m] == (int64_t)v);
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -92,17 +93,21 @@ __global__ void __launch_bounds__(128) embed_bwd_tok_kernel(const int64_t* __res
     __syncthreads();
     int off = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       if (i < w) off += warp_cnt[i];
       total += warp_cnt[i];
     }
     if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = m;
     __syncthreads();
-    if (c < C)
-      for (int j = 0; j < total; ++j) acc += dx[(int64_t)list[j] * C + c];
+    for (int j = 0; j < total; ++j) {
+      const float* row = dx + (int64_t)list[j] * C;
+      if (c0 < C) acc0 += row[c0];
+      if (c1 < C) acc1 += row[c1];
+    }
     __syncthreads();
   }
-  if (c < C) dtok[(int64_t)v * C + c] += acc;
+  if (c0 < C) dtok[(int64_t)v * C + c0] += acc0;
+  if (c1 < C) dtok[(int64_t)v * C + c1] += acc1;
 }
 
 // ---------------------------------------------------------------------------
@@ -245,6 +250,112 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
   }
 }
 
+// Fast path (C % 4 == 0, C <= 128*NV): each lane owns NV float4 column groups for every row its
+// warp visits, so dgamma / dbeta / colsum(dxm) accumulate in registers (no shared-memory atomics);
+// one cross-warp reduction and one global atomic per column per CTA at the end.  The optional
+// colsum(dxm) output is the bias gradient of the GEMM that consumes dxm in the backward pass.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <int NV, typename DyT, typename MT>
+__global__ void __launch_bounds__(256) ln_bwd_fast_kernel(
+    const DyT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, MT* __restrict__ dxm,
+    float* __restrict__ dxm_colsum, uint32_t thr, float inv_keep, uint64_t seed,
+    const uint64_t* __restrict__ seed_dev, uint32_t site, int M, int C) {
+  extern __shared__ float sm[];  // [8][C]
+  if (thr && seed_dev) seed += *seed_dev;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nv = C >> 2;
+  float4 g[NV], ag[NV], ab[NV], am[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int q = lane + 32 * i;
+    g[i] = q < nv ? ld4(gamma + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = ab[i] = am[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.f / (float)C;
+  for (int row = blockIdx.x * 8 + w; row < M; row += gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    const int64_t ro = (int64_t)row * C;
+    float4 d[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        d[i] = ld4(dy + ro + 4 * q);
+        const float4 xv = ld4(x + ro + 4 * q);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        const float4 t = make_float4(d[i].x * g[i].x, d[i].y * g[i].y, d[i].z * g[i].z, d[i].w * g[i].w);
+        s1 += (t.x + t.y) + (t.z + t.w);
+        s2 += (t.x * xh[i].x + t.y * xh[i].y) + (t.z * xh[i].z + t.w * xh[i].w);
+        ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+        ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        float4 v = make_float4(rs * (d[i].x * g[i].x - s1 - xh[i].x * s2), rs * (d[i].y * g[i].y - s1 - xh[i].y * s2),
+                               rs * (d[i].z * g[i].z - s1 - xh[i].z * s2), rs * (d[i].w * g[i].w - s1 - xh[i].w * s2));
+        if (dres) {
+          const float4 r = ld4(dres + ro + 4 * q);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        st4(dx + ro + 4 * q, v);
+        if (dxm) {
+          if (thr) {
+            const u32x4 b = dropout_bits4(seed, site, (uint64_t)row * (uint64_t)nv + (uint64_t)q);
+            v.x = b.x >= thr ? v.x * inv_keep : 0.f;
+            v.y = b.y >= thr ? v.y * inv_keep : 0.f;
+            v.z = b.z >= thr ? v.z * inv_keep : 0.f;
+            v.w = b.w >= thr ? v.w * inv_keep : 0.f;
+          }
+          st4(dxm + ro + 4 * q, v);
+          am[i].x += v.x; am[i].y += v.y; am[i].z += v.z; am[i].w += v.w;
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the three column accumulators, one at a time through sm[8][C]
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    float* out = which == 0 ? dgamma : which == 1 ? dbeta : dxm_colsum;
+    if (out == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) st4(sm + w * C + 4 * q, which == 0 ? ag[i] : which == 1 ? ab[i] : am[i]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += sm[k * C + c];
+      atomicAdd(&out[c], s);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // cross-entropy forward + backward, warp per row
 // ---------------------------------------------------------------------------
@@ -350,26 +461,54 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 }
 
 // ---------------------------------------------------------------------------
-// column sums (bias gradients): 32 columns x 8 row-lanes per CTA
+// column sums (bias gradients): each warp reads whole 128/256-column row segments with 16-byte
+// loads (coalesced), 8 warps stride the rows, shared-memory reduce, one atomic per column per CTA
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int M, int N, int ldx,
                                                      float* __restrict__ out, int rows_per_cta) {
-  __shared__ float red[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
+  constexpr int VEC = sizeof(T) == 4 ? 4 : 8;  // elements per 16-byte load
+  __shared__ float red[8][32 * VEC + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32 * VEC + lane * VEC;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(M, r0 + rows_per_cta);
-  float acc = 0.f;
-  if (col < N)
-    for (int r = r0 + ty; r < r1; r += 8) acc += to_f32(X[(int64_t)r * ldx + col]);
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && col < N) {
-    float s = 0.f;
+  float acc[VEC];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][tx];
-    atomicAdd(&out[col], s);
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const bool vec = (c0 + VEC <= N) && (ldx % VEC == 0) && (((uintptr_t)X & 15) == 0);
+  for (int r = r0 + w; r < r1; r += 8) {
+    const T* p = X + (int64_t)r * ldx + c0;
+    if (vec) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[j]));
+          acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (c0 + j < N) acc[j] += to_f32(p[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red[w][lane * VEC + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int col = blockIdx.x * 32 * VEC + c;
+    if (col < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][c];
+      atomicAdd(&out[col], s);
+    }
   }
 }
 
@@ -473,8 +612,8 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
   if ((int64_t)B * T == 0) return DGPT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dpos) embed_bwd_pos_kernel<<<ceil_div((int64_t)T * C, 256), 256, 0, st>>>(dx, dpos, B, T, C, pos_offset);
-  dim3 grid(V, ceil_div(C, 128));
-  embed_bwd_tok_kernel<<<grid, 128, 0, st>>>(idx, dx, dtok, B * T, C);
+  dim3 grid(V, ceil_div(C, 512));
+  embed_bwd_tok_kernel<<<grid, 256, 0, st>>>(idx, dx, dtok, B * T, C);
   return check_launch("embed_bwd");
 }
 
@@ -494,17 +633,44 @@ int dgpt_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, 
 
 int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
-                void* dxm, int dxm_dtype, float p, uint64_t seed, const uint64_t* seed_dev,
-                uint32_t site, int M, int C, void* stream) {
+                void* dxm, int dxm_dtype, float* dxm_colsum, float p, uint64_t seed,
+                const uint64_t* seed_dev, uint32_t site, int M, int C, void* stream) {
   DGPT_DEVICE_OR_RETURN();
   if (M == 0) return DGPT_OK;
   DGPT_REQUIRE(C > 0 && C <= 6000, "ln_bwd: C=%d unsupported", C);
   DGPT_REQUIRE(p >= 0.f && p < 1.f, "ln_bwd: p=%f", p);
+  DGPT_REQUIRE(!dxm_colsum || dxm, "ln_bwd: dxm_colsum needs dxm");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = min(ceil_div(M, 8), kSMs * 4);
-  const size_t smem = 2 * (size_t)C * sizeof(float);
   const uint32_t thr = dropout_threshold(p);
   const float ik = 1.f / (1.f - p);
+  auto al = [](const void* q, uintptr_t a) { return ((uintptr_t)q & (a - 1)) == 0; };
+  const bool fast = (C % 4 == 0) && C <= 1024 && al(x, 16) && al(gamma, 16) && al(dx, 16) && (!dres || al(dres, 16)) &&
+                    al(dy, dy_dtype == DGPT_F32 ? 16 : 8) && (!dxm || al(dxm, dxm_dtype == DGPT_F32 ? 16 : 8));
+  if (fast) {
+    const int grid = min(ceil_div(M, 8), kSMs * 2);
+    const size_t smem = 8 * (size_t)C * sizeof(float);
+    const int nv = ceil_div(C, 128);
+#define LN_FAST(NV, DyT, MT)                                                                                   \
+  ln_bwd_fast_kernel<NV, DyT, MT><<<grid, 256, smem, st>>>((const DyT*)dy, x, gamma, mean, rstd, dres, dx, dgamma, \
+                                                           dbeta, (MT*)dxm, dxm_colsum, thr, ik, seed, seed_dev, site, M, C)
+#define LN_FAST_T(NV)                                                                \
+  do {                                                                               \
+    if (dy_dtype == DGPT_F32 && dxm_dtype == DGPT_F32) LN_FAST(NV, float, float);    \
+    else if (dy_dtype == DGPT_F32) LN_FAST(NV, float, __nv_bfloat16);                \
+    else if (dxm_dtype == DGPT_F32) LN_FAST(NV, __nv_bfloat16, float);               \
+    else LN_FAST(NV, __nv_bfloat16, __nv_bfloat16);                                  \
+  } while (0)
+    if (nv <= 1) LN_FAST_T(1);
+    else if (nv == 2) LN_FAST_T(2);
+    else if (nv == 3) LN_FAST_T(3);
+    else if (nv == 4) LN_FAST_T(4);
+    else LN_FAST_T(8);
+#undef LN_FAST_T
+#undef LN_FAST
+    return check_launch("ln_bwd_fast");
+  }
+  const int grid = min(ceil_div(M, 8), kSMs * 4);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
 #define LN_BWD(DyT, MT)                                                                             \
   ln_bwd_kernel<DyT, MT><<<grid, 256, smem, st>>>((const DyT*)dy, x, gamma, mean, rstd, dres, dx,   \
                                                   dgamma, dbeta, (MT*)dxm, thr, ik, seed, seed_dev, site, M, C)
@@ -513,7 +679,9 @@ int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma
   else if (dxm_dtype == DGPT_F32) LN_BWD(__nv_bfloat16, float);
   else LN_BWD(__nv_bfloat16, __nv_bfloat16);
 #undef LN_BWD
-  return check_launch("ln_bwd");
+  int rc = check_launch("ln_bwd");
+  if (rc == DGPT_OK && dxm_colsum) rc = dgpt_colsum(dxm, dxm_dtype, M, C, C, dxm_colsum, 1, stream);
+  return rc;
 }
 
 int dgpt_cross_entropy(const float* logits, int ld, const int64_t* targets, float* loss_sum,
@@ -557,9 +725,11 @@ int dgpt_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, int
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
   if (M == 0) return DGPT_OK;
-  const int gy = max(1, min(ceil_div(M, 64), (kSMs * 4) / max(1, ceil_div(N, 32))));
+  const int cols_per_cta = dtype == DGPT_F32 ? 128 : 256;
+  const int gx = ceil_div(N, cols_per_cta);
+  const int gy = max(1, min(ceil_div(M, 64), (kSMs * 4) / gx));
   const int rows_per_cta = ceil_div(M, gy);
-  dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
+  dim3 grid(gx, ceil_div(M, rows_per_cta));
   if (dtype == DGPT_F32)
     colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)X, M, N, ldx, out, rows_per_cta);
   else

@@ -1,10 +1,12 @@
 // Tensor-mode GEMM for sm_100a: bf16 operands staged by TMA (128B swizzle) into a
 // multi-stage shared-memory ring, tcgen05.mma (cta_group::1, 128 x BN x 16) issued
 // by one thread with fp32 accumulators in TMEM, and a fused epilogue
-// (bias / ReLU / ReLU-mask / dropout / residual / fp32+bf16 stores / split-K
-// red.add) read back with tcgen05.ld.  Persistent: one CTA per SM walks the tile
-// list; TMEM holds two accumulators so the epilogue of tile i overlaps the
-// mainloop of tile i+1.
+// (bias / ReLU / ReLU-mask / dropout / residual) whose results leave the SM through
+// swizzled shared-memory staging tiles and TMA stores -- or TMA fp32 reduce-adds for
+// split-K / accumulate -- so the output is written in full 128-byte lines, clipped at the
+// matrix edge by the tensor map, with no per-thread global stores.  Persistent: one CTA
+// per SM walks the tile list; TMEM holds two accumulators so the epilogue of tile i
+// overlaps the mainloop of tile i+1.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
 // issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
@@ -26,142 +28,140 @@ static constexpr int TBM = 128;       // tile M (UMMA M)
 static constexpr int TBK = 64;        // k-block: 64 bf16 = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int kThreads = 192;
-static constexpr size_t kSmemBudget = 200 * 1024;
+static constexpr int kStageBudget = 192 * 1024;
+static constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+
+enum StoreMode { kStoreDirect = 0, kStoreTma = 1, kStoreTmaAdd = 2 };
 
 struct TcParams {
   int M, N, K;
   int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
-  int vec_ok;  // epilogue may use 16-byte accesses
+  int vec_ok;      // epilogue operands (bias / residual / relu_aux) allow 16-byte loads
+  int store_mode;  // StoreMode for D
   Epilogue ep;
 };
 
 template <int BN>
 struct TcCfg {
   static constexpr int kStageBytes = TBM * TBK * 2 + BN * TBK * 2;
-  static constexpr int kStages = (int)(kSmemBudget / kStageBytes) > 8 ? 8 : (int)(kSmemBudget / kStageBytes);
+  static constexpr int kStages = kStageBudget / kStageBytes > 8 ? 8 : kStageBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // --------------------------------------------------------------------------
-// epilogue for one 32-column chunk of one accumulator row
+// epilogue math on 32 consecutive columns [n, n+32) of accumulator row m (all in registers)
 // --------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int vec_ok, int m, int n, uint32_t (&r)[32]) {
+__device__ __forceinline__ void epilogue_math32(const Epilogue& e, int vec_ok, int m, int n, float (&v)[32]) {
   if (m >= e.M) return;
-  if (vec_ok && n + 32 <= e.N) {
-    float v[32];
+  if (!(vec_ok && n + 32 <= e.N)) {  // ragged edge / unaligned operands: guarded scalar path (fully unrolled)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (e.first_split && e.bias) {
+    for (int j = 0; j < 32; ++j)
+      if (n + j < e.N) v[j] = epilogue_value(e, m, n + j, v[j]);
+    return;
+  }
+  if (e.first_split && e.bias) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
-    if (e.relu) {
+  }
+  if (e.relu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (e.relu_aux) {
-      if (e.aux_dtype == DGPT_BF16) {
-        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (e.relu_aux) {
+    if (e.aux_dtype == DGPT_BF16) {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 a = __ldg(ap + j);
-          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = __ldg(ap + j);
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            const uint32_t lo = w[t] & 0xFFFFu, hi = w[t] >> 16;
-            if (!(lo != 0 && lo < 0x8000u)) v[j * 8 + t * 2] = 0.f;
-            if (!(hi != 0 && hi < 0x8000u)) v[j * 8 + t * 2 + 1] = 0.f;
-          }
-        }
-      } else {
-        const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(ap + j);
-          if (!(a.x > 0.f)) v[4 * j] = 0.f;
-          if (!(a.y > 0.f)) v[4 * j + 1] = 0.f;
-          if (!(a.z > 0.f)) v[4 * j + 2] = 0.f;
-          if (!(a.w > 0.f)) v[4 * j + 3] = 0.f;
-        }
-      }
-    }
-    if (e.thr) {
-      const uint64_t q0 = ((uint64_t)m * (uint64_t)e.N + (uint64_t)n) >> 2;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const u32x4 b = dropout_bits4(e.seed, e.site, q0 + j);
-        v[4 * j] = b.x >= e.thr ? v[4 * j] * e.inv_keep : 0.f;
-        v[4 * j + 1] = b.y >= e.thr ? v[4 * j + 1] * e.inv_keep : 0.f;
-        v[4 * j + 2] = b.z >= e.thr ? v[4 * j + 2] * e.inv_keep : 0.f;
-        v[4 * j + 3] = b.w >= e.thr ? v[4 * j + 3] * e.inv_keep : 0.f;
-      }
-    }
-    if (e.first_split && e.residual) {
-      const float4* rp = reinterpret_cast<const float4*>(e.residual + (int64_t)m * e.ldr + n);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 a = __ldg(rp + j);
-        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-      }
-    }
-    if (e.d_dtype == DGPT_F32) {
-      float* d = reinterpret_cast<float*>(e.D) + (int64_t)m * e.ldd + n;
-      if (e.atomic) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(d + j, v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (e.accumulate) {
-            const float4 c = reinterpret_cast<float4*>(d)[j];
-            o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-            v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
-          }
-          reinterpret_cast<float4*>(d)[j] = o;
+        for (int t = 0; t < 4; ++t) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t lo = w[t] & 0xFFFFu, hi = w[t] >> 16;
+          if (!(lo != 0 && lo < 0x8000u)) v[j * 8 + t * 2] = 0.f;
+          if (!(hi != 0 && hi < 0x8000u)) v[j * 8 + t * 2 + 1] = 0.f;
         }
       }
     } else {
-      uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + (int64_t)m * e.ldd + n);
+      const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-        d[j] = o;
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = __ldg(ap + j);
+        if (!(a.x > 0.f)) v[4 * j] = 0.f;
+        if (!(a.y > 0.f)) v[4 * j + 1] = 0.f;
+        if (!(a.z > 0.f)) v[4 * j + 2] = 0.f;
+        if (!(a.w > 0.f)) v[4 * j + 3] = 0.f;
       }
     }
-    if (e.D2) {
-      if (e.d2_dtype == DGPT_F32) {
-        float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.D2) + (int64_t)m * e.ldd2 + n);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {
-        uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D2) + (int64_t)m * e.ldd2 + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-          o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-          d[j] = o;
-        }
-      }
-    }
-    return;
   }
-  // ragged / unaligned tail: element-wise
-#pragma unroll 1
+  if (e.thr) {
+    const uint64_t q0 = ((uint64_t)m * (uint64_t)e.N + (uint64_t)n) >> 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u32x4 b = dropout_bits4(e.seed, e.site, q0 + j);
+      v[4 * j] = b.x >= e.thr ? v[4 * j] * e.inv_keep : 0.f;
+      v[4 * j + 1] = b.y >= e.thr ? v[4 * j + 1] * e.inv_keep : 0.f;
+      v[4 * j + 2] = b.z >= e.thr ? v[4 * j + 2] * e.inv_keep : 0.f;
+      v[4 * j + 3] = b.w >= e.thr ? v[4 * j + 3] * e.inv_keep : 0.f;
+    }
+  }
+  if (e.first_split && e.residual) {
+    const float4* rp = reinterpret_cast<const float4*>(e.residual + (int64_t)m * e.ldr + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(rp + j);
+      v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+    }
+  }
+}
+
+// element-wise stores for outputs the TMA cannot address (unaligned pitch) and for the optional D2
+__device__ __forceinline__ void direct_store32(const Epilogue& e, bool main_out, int m, int n, const float (&v)[32]) {
+  if (m >= e.M) return;
+#pragma unroll
   for (int j = 0; j < 32; ++j) {
-    if (n + j < e.N) epilogue_store(e, m, n + j, epilogue_value(e, m, n + j, __uint_as_float(r[j])));
+    if (n + j >= e.N) continue;
+    if (main_out) {
+      const int64_t i = (int64_t)m * e.ldd + n + j;
+      if (e.d_dtype == DGPT_F32) {
+        float* d = reinterpret_cast<float*>(e.D);
+        if (e.atomic) atomicAdd(d + i, v[j]);
+        else d[i] = e.accumulate ? d[i] + v[j] : v[j];
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(e.D)[i] = __float2bfloat16_rn(v[j]);
+      }
+    } else {
+      const int64_t i = (int64_t)m * e.ldd2 + n + j;
+      if (e.d2_dtype == DGPT_F32) reinterpret_cast<float*>(e.D2)[i] = v[j];
+      else reinterpret_cast<__nv_bfloat16*>(e.D2)[i] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// one row (128 bytes) of a 32-row SWIZZLE_128B staging tile
+__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int row, const float (&v)[32]) {
+  uint8_t* rp = tile + row * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(rp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int half, const float (&v)[32]) {
+  uint8_t* rp = tile + row * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 w;
+    w.x = pack2(v[8 * j], v[8 * j + 1]); w.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+    w.z = pack2(v[8 * j + 4], v[8 * j + 5]); w.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(rp + (((half * 4 + j) ^ (row & 7)) << 4)) = w;
   }
 }
 
@@ -170,7 +170,8 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int vec_ok, 
 // --------------------------------------------------------------------------
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = TBM * TBK * 2;
@@ -180,7 +181,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + (size_t)kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 8 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -191,6 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
+    if (p.store_mode != kStoreDirect) prefetch_tensormap(&map_d);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -279,31 +282,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ------------------------------ epilogue -------------------------------
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    uint8_t* my_stage = staging + quad * 8192;
+    int sbuf = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
     Epilogue ep = p.ep;
     epilogue_resolve_seed(ep);
+    const bool bf16_out = ep.d_dtype == DGPT_BF16;
+    const int mode = p.store_mode;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
       ep.first_split = (ks == 0);
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      const int m = m0 + quad * 32 + lane;
+      const int mrow0 = m0 + quad * 32;
+      const int m = mrow0 + lane;
       const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      if (mode != kStoreDirect && bf16_out) {
+        // 64 columns (= 128 bytes of bf16) per staging tile
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (n0 + c >= p.N) break;
-        uint32_t r[32];
-        tmem_ld32(row_addr + c, r);
-        tmem_ld_wait();
-        epilogue_chunk32(ep, p.vec_ok, m, n0 + c, r);
+        for (int c = 0; c < BN; c += 64) {
+          if (n0 + c >= p.N || mrow0 >= p.M) break;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(row_addr + c, r0);
+          tmem_ld32(row_addr + c + 32, r1);
+          uint8_t* tile = my_stage + sbuf * 4096;
+          if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has drained this buffer
+          __syncwarp();
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+          epilogue_math32(ep, p.vec_ok, m, n0 + c, v);
+          if (ep.D2) direct_store32(ep, false, m, n0 + c, v);
+          stage_half_row_bf16(tile, lane, 0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+          epilogue_math32(ep, p.vec_ok, m, n0 + c + 32, v);
+          if (ep.D2) direct_store32(ep, false, m, n0 + c + 32, v);
+          stage_half_row_bf16(tile, lane, 1, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_d, tile, n0 + c, mrow0);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N || mrow0 >= p.M) break;
+          uint32_t r[32];
+          tmem_ld32(row_addr + c, r);
+          uint8_t* tile = my_stage + sbuf * 4096;
+          if (mode != kStoreDirect) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_math32(ep, p.vec_ok, m, n0 + c, v);
+          if (ep.D2) direct_store32(ep, false, m, n0 + c, v);
+          if (mode == kStoreDirect) {
+            direct_store32(ep, true, m, n0 + c, v);
+          } else {
+            stage_row_f32(tile, lane, v);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n0 + c, mrow0);
+              else tma_store_2d(&map_d, tile, n0 + c, mrow0);
+              bulk_commit();
+            }
+            sbuf ^= 1;
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();  // all output tiles have landed before the CTA retires
   }
 
   tc_fence_before();
@@ -337,23 +401,25 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent `inner`, `outer` rows of pitch ld elements;
-// box = 64 x box_outer elements, 128-byte swizzle, zero fill out of bounds.
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+// 2-D tensor map with 128-byte swizzle and zero fill out of bounds: inner (contiguous) extent `inner`
+// elements, `outer` rows of pitch ld elements, box = box_inner x box_outer elements (box_inner * esize == 128).
+int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, int64_t inner, int64_t outer, int64_t ld,
+                 int box_inner, int box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
     return DGPT_E_DEVICE;
   }
-  DGPT_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0,
-               "tensor-core operand needs a 16-byte aligned base and row pitch (ld=%lld)", (long long)ld);
+  const int esize = dtype == DGPT_F32 ? 4 : 2;
+  DGPT_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * esize) % 16 == 0,
+               "TMA needs a 16-byte aligned base and row pitch (ld=%lld elements of %d bytes)", (long long)ld, esize);
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dtype == DGPT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r,
               (long long)inner, (long long)outer, (long long)ld);
@@ -362,8 +428,13 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return DGPT_OK;
 }
 
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
+}
+
 template <int BN, int A_MN, int B_MN>
-static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid, cudaStream_t st) {
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const TcParams& p, int grid,
+                      cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -375,7 +446,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcPara
     }
     attr_done = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, md, p);
   return check_launch("gemm_tc");
 }
 
@@ -406,11 +477,10 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("gemm_tc: memset: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
   }
   auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-  p.vec_ok = (a->N % 4 == 0) && al16(a->D) && (a->ldd % 8 == 0) && (!a->D2 || (al16(a->D2) && a->ldd2 % 8 == 0)) &&
-             (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0)) &&
+  p.vec_ok = (a->N % 4 == 0) && (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0)) &&
              (!a->relu_aux || (al16(a->relu_aux) && a->ld_aux % 8 == 0));
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, md;
   int rc;
   if (a_mn) rc = make_tmap_bf16_2d(&ma, a->A, a->M, a->K, a->lda, 64);
   else rc = make_tmap_bf16_2d(&ma, a->A, a->K, a->M, a->lda, TBM);
@@ -418,14 +488,24 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (b_mn) rc = make_tmap_bf16_2d(&mb, a->B, a->N, a->K, a->ldb, 64);
   else rc = make_tmap_bf16_2d(&mb, a->B, a->K, a->N, a->ldb, BN);
   if (rc) return rc;
+  // output through TMA when its pitch allows it (always true for the model's buffers)
+  const int desz = a->d_dtype == DGPT_F32 ? 4 : 2;
+  p.store_mode = kStoreDirect;
+  if (al16(a->D) && ((int64_t)a->ldd * desz) % 16 == 0) {
+    rc = make_tmap_2d(&md, a->D, a->d_dtype, a->N, a->M, a->ldd, 128 / desz, 32);
+    if (rc) return rc;
+    p.store_mode = (p.ep.atomic || a->accumulate) ? kStoreTmaAdd : kStoreTma;
+  } else {
+    md = ma;
+  }
 
   const int total = m_tiles * n_tiles * p.split_k;
   const int grid = min(total, sms);
 #define TC_DISPATCH(BN_)                                                                   \
   if (BN == BN_) {                                                                         \
-    if (!a_mn && !b_mn) return launch_cfg<BN_, 0, 0>(ma, mb, p, grid, st);                 \
-    if (!a_mn && b_mn) return launch_cfg<BN_, 0, 1>(ma, mb, p, grid, st);                  \
-    return launch_cfg<BN_, 1, 1>(ma, mb, p, grid, st);                                     \
+    if (!a_mn && !b_mn) return launch_cfg<BN_, 0, 0>(ma, mb, md, p, grid, st);             \
+    if (!a_mn && b_mn) return launch_cfg<BN_, 0, 1>(ma, mb, md, p, grid, st);              \
+    return launch_cfg<BN_, 1, 1>(ma, mb, md, p, grid, st);                                 \
   }
   TC_DISPATCH(64)
   TC_DISPATCH(128)

@@ -318,7 +318,8 @@ class Runner:
         # ---- FFN2: y = h W2^T + b2 (dropout, residual) ----
         self._gemm(gm, h, self.g(L["ffn"][3]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                    split_k=self._splits(C, F, M, sm))
-        ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
+        if li == len(self.spec["layers"]) - 1:  # other layers: fused into the LN1 backward of layer li+1
+            ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
         dh = self.buf("dh", (M, F))
         self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN, relu_aux=h)
         # ---- FFN1: h = relu(xn2 W1^T + b1) ----
@@ -330,11 +331,10 @@ class Runner:
         # ---- LN2 backward + residual-gradient add + masked copy for the proj GEMMs ----
         g1 = g_other
         ops.raw_ln_bwd(dxn, x1, self.f(L["ln2"][0]), mean2, rstd2, g, g1, self.g(L["ln2"][0]), self.g(L["ln2"][1]),
-                       dxm=gm, dropout=self._drop(L["p"], 4 * li + 1, training))
+                       dxm=gm, dropout=self._drop(L["p"], 4 * li + 1, training), dxm_colsum=self.g(L["proj"][1]))
         # ---- proj: y = att Wp^T + bp (dropout, residual) ----
         self._gemm(gm, att, self.g(L["proj"][0]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                    split_k=self._splits(C, D, M, sm))
-        ops.raw_colsum(gm, self.g(L["proj"][1]), accumulate=True)
         datt = self.buf("datt", (M, D))
         self._gemm(gm, self.w(L["proj"][0]), datt, b_major=MAJOR_MN)
         # ---- attention ----
@@ -353,7 +353,8 @@ class Runner:
         g0 = g
         ops.raw_ln_bwd(dxn, x_in, self.f(L["ln1"][0]), mean1, rstd1, g1, g0, self.g(L["ln1"][0]),
                        self.g(L["ln1"][1]), dxm=gm if nxt is not None else None,
-                       dropout=self._drop(nxt["p"], 4 * (li - 1) + 2, training) if nxt is not None else None)
+                       dropout=self._drop(nxt["p"], 4 * (li - 1) + 2, training) if nxt is not None else None,
+                       dxm_colsum=self.g(nxt["ffn"][4]) if nxt is not None else None)
         return g0
 
     # ------------------------------------------------------------------ #

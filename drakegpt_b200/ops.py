@@ -154,14 +154,14 @@ def raw_ln_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     return y
 
 
-def raw_ln_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxm=None, dropout=None):
+def raw_ln_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxm=None, dropout=None, dxm_colsum=None):
     M, Cdim = x.shape
     p, seed, site, sd = 0.0, 0, 0, None
     if dropout is not None and dropout.p > 0.0:
         p, seed, site, sd = dropout.p, dropout.seed, dropout.site, _p(dropout.seed_dev)
     check(_lib.lib().dgpt_ln_bwd(_p(dy), _DT[dy.dtype], _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx),
                                  _p(dgamma), _p(dbeta), _p(dxm), _DT[dxm.dtype] if dxm is not None else 0,
-                                 p, seed, sd, site, M, Cdim, _stream()), "dgpt_ln_bwd")
+                                 _p(dxm_colsum), p, seed, sd, site, M, Cdim, _stream()), "dgpt_ln_bwd")
 
 
 def raw_dropout_scale(x, out, dropout=None, relu_aux=None):

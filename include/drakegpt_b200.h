@@ -48,7 +48,9 @@ int dgpt_sm_count(void);
 /* ------------------------------------------------------------------------- *
  * Counter-based dropout mask shared by every kernel (forward and backward
  * regenerate it; nothing is stored):  keep(seed, site, i) =
- *   philox4x32_10(key=seed, ctr=(i/4, site))[i%4] >= p * 2^32.
+ *   lane16(splitmix64(seed + (i/4)*0x9E3779B97F4A7C15 + (site+1)*0xD1B54A32D192ED03), i%4)
+ *     >= round(p * 65536)
+ * (four consecutive elements share one 64-bit hash, 16 bits each).
  * Replaces nn.Dropout at src/model_component.py:324,376/401,434/454.
  * Every entry that takes `seed` also takes `seed_dev`: an optional DEVICE
  * uint64 added to `seed` when the kernel runs, so that a captured CUDA graph
@@ -84,14 +86,16 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
  *      gamma == NULL: y = cast(x) (identity; mean/rstd untouched).
  * bwd: dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are ACCUMULATED.
  *      Optional fused second output for the next backward GEMM:
- *      dxm = dx * keep(site)/(1-p) cast to dxm_dtype (dxm may be NULL).
+ *      dxm = dx * keep(site)/(1-p) cast to dxm_dtype (dxm may be NULL), and
+ *      dxm_colsum[c] += sum_m dxm[m,c] (may be NULL): the bias gradient of the
+ *      Linear whose backward GEMMs consume dxm.
  * ------------------------------------------------------------------------- */
 int dgpt_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                 float* mean, float* rstd, int M, int C, float eps, void* stream);
 int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
-                void* dxm, int dxm_dtype, float p, uint64_t seed, const uint64_t* seed_dev,
-                uint32_t site, int M, int C, void* stream);
+                void* dxm, int dxm_dtype, float* dxm_colsum, float p, uint64_t seed,
+                const uint64_t* seed_dev, uint32_t site, int M, int C, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * GEMM with fused epilogue.   acc[m,n] = sum_k A(m,k) * B(n,k)
