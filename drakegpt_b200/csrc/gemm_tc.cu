@@ -8,14 +8,15 @@
 // per SM walks the tile list; TMEM holds two accumulators so the epilogue of tile i
 // overlaps the mainloop of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
-// issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant).
 //
 // Operand layouts: K-major ([rows, K], K contiguous: activations, nn.Linear
 // weights) and MN-major ([K, rows], rows contiguous: the transposed views that
 // dgrad / wgrad need) are both fed straight from the row-major tensors -- no
 // transposed copies are ever written to HBM.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -27,9 +28,9 @@ using namespace ptx;
 static constexpr int TBM = 128;       // tile M (UMMA M)
 static constexpr int TBK = 64;        // k-block: 64 bf16 = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int kThreads = 192;
-static constexpr int kStageBudget = 192 * 1024;
-static constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+static constexpr int kThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps
+static constexpr int kStageBudget = 160 * 1024;
+static constexpr int kStagingBytes = 8 * 2 * 4096;  // 8 epilogue warps x 2 buffers x (32 rows x 128 B)
 
 enum StoreMode { kStoreDirect = 0, kStoreTma = 1, kStoreTmaAdd = 2 };
 
@@ -38,6 +39,10 @@ struct TcParams {
   int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
   int vec_ok;      // epilogue operands (bias / residual / relu_aux) allow 16-byte loads
   int store_mode;  // StoreMode for D
+#ifdef DGPT_GEMM_TS
+  long long* ts;   // cycle stamps of (block 0, first epilogue warp, lane 0) for the first tiles (debug builds)
+#endif
+  int debug;       // DGPT_GEMM_DEBUG: 1 = epilogue skipped, 2 = no TMA loads / MMAs (timing experiments only)
   Epilogue ep;
 };
 
@@ -46,38 +51,64 @@ struct TcCfg {
   static constexpr int kStageBytes = TBM * TBK * 2 + BN * TBK * 2;
   static constexpr int kStages = kStageBudget / kStageBytes > 8 ? 8 : kStageBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + 256 /*barriers*/;
 };
 
 // --------------------------------------------------------------------------
-// epilogue math on 32 consecutive columns [n, n+32) of accumulator row m (all in registers)
+// epilogue math on 32 consecutive columns [n, n+32) of accumulator row m (all in registers).
+// Fast path only: n + 32 <= N, 16-byte aligned operands.  Keep this small -- the kernel's
+// instruction footprint must stay inside the instruction cache (an earlier version that
+// unrolled the ragged path 32x was 180 KB of SASS and stalled on instruction fetch).
 // --------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_math32(const Epilogue& e, int vec_ok, int m, int n, float (&v)[32]) {
-  if (m >= e.M) return;
-  if (!(vec_ok && n + 32 <= e.N)) {  // ragged edge / unaligned operands: guarded scalar path (fully unrolled)
+// `pre` holds the chunk's residual (8 x float4) or ReLU-mask operand (4 x uint4 of bf16 / 8 x float4 of
+// fp32), fetched one chunk ahead; `bias_s` is the tile's bias slice in shared memory.  (With ~226 KB
+// of shared memory in use the L1 data cache is nearly gone: an un-prefetched global load here costs a
+// full L2 round trip per chunk on the only warp of the scheduler, which is what bounded the epilogue.)
+// EPI: compile-time feature mask of the fused epilogue (kEpiBias | kEpiRelu | ...), or -1 to test the
+// run-time flags.  The specialisations matter: with run-time flags the compiler if-converts the whole
+// body (~600 predicated instructions per 32-column step, measured 700 cycles) instead of ~100.
+enum { kEpiBias = 1, kEpiRelu = 2, kEpiAux = 4, kEpiDrop = 8, kEpiRes = 16 };
+template <int EPI> __device__ __forceinline__ bool epi_has(int bit, bool runtime) { return EPI < 0 ? runtime : (EPI & bit) != 0; }
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int m, int n, uint4 (&pre)[8]) {
+  if (e.first_split && epi_has<EPI>(kEpiRes, e.residual != nullptr)) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.residual + (int64_t)m * e.ldr + n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < e.N) v[j] = epilogue_value(e, m, n + j, v[j]);
-    return;
-  }
-  if (e.first_split && e.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
-  }
-  if (e.relu) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-  if (e.relu_aux) {
+    for (int j = 0; j < 8; ++j) pre[j] = __ldg(rp + j);
+  } else if (epi_has<EPI>(kEpiAux, e.relu_aux != nullptr)) {
     if (e.aux_dtype == DGPT_BF16) {
       const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
 #pragma unroll
+      for (int j = 0; j < 4; ++j) pre[j] = __ldg(ap + j);
+    } else {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[j] = __ldg(ap + j);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_math32(const Epilogue& e, int m, int n, float (&v)[32], const float* bias_s,
+                                                const uint4 (&pre)[8]) {
+  if (e.first_split && epi_has<EPI>(kEpiBias, e.bias != nullptr)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);  // shared-memory broadcast
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (epi_has<EPI>(kEpiRelu, e.relu != 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (epi_has<EPI>(kEpiAux, e.relu_aux != nullptr)) {
+    if (e.aux_dtype == DGPT_BF16) {
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 a = __ldg(ap + j);
-        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t w[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           // bf16 > 0  <=>  sign bit clear and magnitude non-zero
@@ -87,18 +118,16 @@ __device__ __forceinline__ void epilogue_math32(const Epilogue& e, int vec_ok, i
         }
       }
     } else {
-      const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 a = __ldg(ap + j);
-        if (!(a.x > 0.f)) v[4 * j] = 0.f;
-        if (!(a.y > 0.f)) v[4 * j + 1] = 0.f;
-        if (!(a.z > 0.f)) v[4 * j + 2] = 0.f;
-        if (!(a.w > 0.f)) v[4 * j + 3] = 0.f;
+        if (!(__uint_as_float(pre[j].x) > 0.f)) v[4 * j] = 0.f;
+        if (!(__uint_as_float(pre[j].y) > 0.f)) v[4 * j + 1] = 0.f;
+        if (!(__uint_as_float(pre[j].z) > 0.f)) v[4 * j + 2] = 0.f;
+        if (!(__uint_as_float(pre[j].w) > 0.f)) v[4 * j + 3] = 0.f;
       }
     }
   }
-  if (e.thr) {
+  if (epi_has<EPI>(kEpiDrop, e.thr != 0)) {
     const uint64_t q0 = ((uint64_t)m * (uint64_t)e.N + (uint64_t)n) >> 2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -109,35 +138,40 @@ __device__ __forceinline__ void epilogue_math32(const Epilogue& e, int vec_ok, i
       v[4 * j + 3] = b.w >= e.thr ? v[4 * j + 3] * e.inv_keep : 0.f;
     }
   }
-  if (e.first_split && e.residual) {
-    const float4* rp = reinterpret_cast<const float4*>(e.residual + (int64_t)m * e.ldr + n);
+  if (e.first_split && epi_has<EPI>(kEpiRes, e.residual != nullptr)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 a = __ldg(rp + j);
-      v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+      v[4 * j] += __uint_as_float(pre[j].x); v[4 * j + 1] += __uint_as_float(pre[j].y);
+      v[4 * j + 2] += __uint_as_float(pre[j].z); v[4 * j + 3] += __uint_as_float(pre[j].w);
     }
   }
 }
 
-// element-wise stores for outputs the TMA cannot address (unaligned pitch) and for the optional D2
-__device__ __forceinline__ void direct_store32(const Epilogue& e, bool main_out, int m, int n, const float (&v)[32]) {
+// Ragged edge (n + 32 > N), unaligned operands, outputs the TMA cannot address, and the optional
+// second output: one compact element-wise loop over a local copy of the 32 values.
+// (Epilogue BY VALUE: a reference would pin the caller's copy in local memory, turning every flag test of
+// the fast path into a local-memory load.)
+__device__ __noinline__ void epilogue_slow32(const Epilogue e, float* v, int m, int n, int store_main) {
   if (m >= e.M) return;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 32; ++j) {
-    if (n + j >= e.N) continue;
-    if (main_out) {
+    if (n + j >= e.N) break;
+    const float x = epilogue_value(e, m, n + j, v[j]);
+    v[j] = x;
+    if (store_main) {
       const int64_t i = (int64_t)m * e.ldd + n + j;
       if (e.d_dtype == DGPT_F32) {
         float* d = reinterpret_cast<float*>(e.D);
-        if (e.atomic) atomicAdd(d + i, v[j]);
-        else d[i] = e.accumulate ? d[i] + v[j] : v[j];
+        if (e.atomic) atomicAdd(d + i, x);
+        else d[i] = e.accumulate ? d[i] + x : x;
       } else {
-        reinterpret_cast<__nv_bfloat16*>(e.D)[i] = __float2bfloat16_rn(v[j]);
+        reinterpret_cast<__nv_bfloat16*>(e.D)[i] = __float2bfloat16_rn(x);
       }
-    } else {
+    }
+    if (e.D2) {
       const int64_t i = (int64_t)m * e.ldd2 + n + j;
-      if (e.d2_dtype == DGPT_F32) reinterpret_cast<float*>(e.D2)[i] = v[j];
-      else reinterpret_cast<__nv_bfloat16*>(e.D2)[i] = __float2bfloat16_rn(v[j]);
+      if (e.d2_dtype == DGPT_F32) reinterpret_cast<float*>(e.D2)[i] = x;
+      else reinterpret_cast<__nv_bfloat16*>(e.D2)[i] = __float2bfloat16_rn(x);
     }
   }
 }
@@ -168,7 +202,7 @@ __device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int 
 // --------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, TcParams p) {
@@ -178,11 +212,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int kBBytes = BN * TBK * 2;
   constexpr uint32_t kIdesc = make_idesc_bf16(TBM, BN, A_MN, B_MN);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + (size_t)kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 8 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  float* bias_s = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + Cfg::kBiasBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -200,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -222,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
         const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -257,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * Cfg::kStageBytes);
@@ -281,8 +315,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ------------------------------ epilogue -------------------------------
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
-    uint8_t* my_stage = staging + quad * 8192;
+    // Eight warps: TMEM lane quadrant = warp % 4 (hardware rule), and the two warps of a quadrant
+    // split the tile's columns.  Two warps per scheduler hide each other's fixed latencies
+    // (measured per 32-column step of one warp: tcgen05.ld+wait ~590 cycles, bias/ReLU ~400,
+    // pack+STS ~190, fence+TMA store ~260); the TMEM load of step i+1 is issued before step i's math.
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lanes [32*quad, 32*quad+32)
+    const int half = ew >> 2;    // columns [half*BN/2, (half+1)*BN/2)
+    constexpr int kCols = BN / 2;
+    uint8_t* my_stage = staging + ew * 8192;
     int sbuf = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
@@ -294,73 +335,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
       ep.first_split = (ks == 0);
+      const int mrow0 = (p.debug & 1) ? p.M : m0 + quad * 32;  // debug bit 0: skip all epilogue work
+      const int m = mrow0 + lane;
+      const bool row_ok = m < p.M;
+      // stage this tile's bias slice (each warp an eighth) while the accumulator is still being produced
+      float* bias_t = bias_s + acc * BN;
+      if (p.vec_ok && ep.first_split && epi_has<EPI>(kEpiBias, ep.bias != nullptr)) {
+        const int col = ew * (BN / 8) + lane * 4;
+        if (lane * 4 < BN / 8 && n0 + col < p.N)
+          *reinterpret_cast<float4*>(bias_t + col) = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + col));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+      const int nbeg = n0 + half * kCols;
+      const bool active = mrow0 < p.M && nbeg < p.N;
+      uint4 pre[8];
+      if (p.vec_ok && row_ok && nbeg + 32 <= p.N) epilogue_prefetch<EPI>(ep, m, nbeg, pre);
+#ifdef DGPT_GEMM_TS
+      const bool stamp = p.ts && blockIdx.x == 0 && warp == 2 && lane == 0 && t < 3 * (int)gridDim.x;
+      long long* tsp = p.ts + (t / gridDim.x) * 64;
+      int tsi = 0;
+#define TS_MARK() do { if (stamp) tsp[tsi++] = clock64(); } while (0)
+#else
+#define TS_MARK() do { } while (0)
+#endif
+      TS_MARK();
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      const int mrow0 = m0 + quad * 32;
-      const int m = mrow0 + lane;
-      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      if (mode != kStoreDirect && bf16_out) {
-        // 64 columns (= 128 bytes of bf16) per staging tile
+      TS_MARK();
+      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kCols);
+      // 32 accumulator columns per step; a staging tile (32 rows x 128 B) holds 32 fp32 or 64 bf16
+      // columns, so bf16 output issues one TMA store every second step
+      uint8_t* tile = my_stage + sbuf * 4096;
+      uint32_t r[32];
+#ifdef DGPT_GEMM_TS
+      {  // micro-benchmark: 1 load vs 4 back-to-back loads (latency- or throughput-bound?)
+        uint32_t q0[32], q1[32], q2[32], q3[32];
+        TS_MARK();
+        tmem_ld32(row_addr, q0);
+        tmem_ld_wait();
+        TS_MARK();
+        tmem_ld32(row_addr, q0); tmem_ld32(row_addr + 32, q1); tmem_ld32(row_addr + 64, q2); tmem_ld32(row_addr + 96, q3);
+        tmem_ld_wait();
+        TS_MARK();
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x ^= q0[j] ^ q1[j] ^ q2[j] ^ q3[j];
+        if (x == 0x12345678u) tile[0] = 1;
+        TS_MARK();
+      }
+#endif
+      if (active) tmem_ld32(row_addr, r);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
-          if (n0 + c >= p.N || mrow0 >= p.M) break;
-          uint32_t r0[32], r1[32];
-          tmem_ld32(row_addr + c, r0);
-          tmem_ld32(row_addr + c + 32, r1);
-          uint8_t* tile = my_stage + sbuf * 4096;
+      for (int c = 0; c < kCols && active; c += 32) {
+        const int n = nbeg + c;
+        if (n >= p.N) break;
+        const bool opens_tile = !bf16_out || (c & 32) == 0;
+        if (mode != kStoreDirect && opens_tile) {
+          tile = my_stage + sbuf * 4096;
           if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has drained this buffer
           __syncwarp();
-          tmem_ld_wait();
-          float v[32];
+        }
+        TS_MARK();
+        tmem_ld_wait();
+        TS_MARK();
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-          epilogue_math32(ep, p.vec_ok, m, n0 + c, v);
-          if (ep.D2) direct_store32(ep, false, m, n0 + c, v);
-          stage_half_row_bf16(tile, lane, 0, v);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool has_next = c + 32 < kCols && n + 32 < p.N;
+        if (has_next) tmem_ld32(row_addr + c + 32, r);  // in flight during this step's math
+        if (p.vec_ok && n + 32 <= p.N && row_ok) {
+          epilogue_math32<EPI>(ep, m, n, v, bias_t + half * kCols + c, pre);
+        } else {
+          float tmp[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-          epilogue_math32(ep, p.vec_ok, m, n0 + c + 32, v);
-          if (ep.D2) direct_store32(ep, false, m, n0 + c + 32, v);
-          stage_half_row_bf16(tile, lane, 1, v);
+          for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+          epilogue_slow32(ep, tmp, m, n, mode == kStoreDirect);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tmp[j];
+        }
+        // operands of the next step: in flight during the staging / store below and the next TMEM wait
+        if (has_next && p.vec_ok && row_ok && n + 64 <= p.N) epilogue_prefetch<EPI>(ep, m, n + 32, pre);
+        TS_MARK();
+        if (mode == kStoreDirect) continue;
+        const bool closes_tile = !bf16_out || (c & 32) != 0 || !has_next;
+        if (bf16_out) stage_half_row_bf16(tile, lane, (c >> 5) & 1, v);
+        else stage_row_f32(tile, lane, v);
+        TS_MARK();
+        if (closes_tile) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_d, tile, n0 + c, mrow0);
+            const int ncol = bf16_out ? nbeg + (c & ~63) : n;
+            if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, ncol, mrow0);
+            else tma_store_2d(&map_d, tile, ncol, mrow0);
             bulk_commit();
           }
           sbuf ^= 1;
         }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n0 + c >= p.N || mrow0 >= p.M) break;
-          uint32_t r[32];
-          tmem_ld32(row_addr + c, r);
-          uint8_t* tile = my_stage + sbuf * 4096;
-          if (mode != kStoreDirect) {
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_math32(ep, p.vec_ok, m, n0 + c, v);
-          if (ep.D2) direct_store32(ep, false, m, n0 + c, v);
-          if (mode == kStoreDirect) {
-            direct_store32(ep, true, m, n0 + c, v);
-          } else {
-            stage_row_f32(tile, lane, v);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n0 + c, mrow0);
-              else tma_store_2d(&map_d, tile, n0 + c, mrow0);
-              bulk_commit();
-            }
-            sbuf ^= 1;
-          }
-        }
+        TS_MARK();
       }
       tc_fence_before();
       __syncwarp();
@@ -432,13 +504,13 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int EPI>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const TcParams& p, int grid,
                       cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -446,7 +518,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
     }
     attr_done = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, md, p);
+  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, md, p);
   return check_launch("gemm_tc");
 }
 
@@ -459,8 +531,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (sms <= 0) sms = 148;
   const int m_tiles = ceil_div(a->M, TBM);
   int BN = 256;
-  if (a->N <= 64) BN = 64;
-  else if (a->N <= 128 || a->N % 256 != 0) BN = 128;
+  if (a->N <= 128 || a->N % 256 != 0) BN = 128;
   if (BN == 256 && m_tiles * (a->N / 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
   const int n_tiles = ceil_div(a->N, BN);
   TcParams p;
@@ -480,6 +551,17 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   p.vec_ok = (a->N % 4 == 0) && (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0)) &&
              (!a->relu_aux || (al16(a->relu_aux) && a->ld_aux % 8 == 0));
 
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DGPT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+#ifdef DGPT_GEMM_TS
+    static long long* ts = nullptr;
+    if (!ts) { cudaMalloc(&ts, 3 * 64 * sizeof(long long)); }
+    cudaMemset(ts, 0, 3 * 64 * sizeof(long long));
+    p.ts = ts;
+#endif
+  }
   CUtensorMap ma, mb, md;
   int rc;
   if (a_mn) rc = make_tmap_bf16_2d(&ma, a->A, a->M, a->K, a->lda, 64);
@@ -498,19 +580,54 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   } else {
     md = ma;
   }
+  if (p.store_mode == kStoreDirect || a->D2 || (a->residual && a->relu_aux)) p.vec_ok = 0;  // everything through the compact element-wise path
 
   const int total = m_tiles * n_tiles * p.split_k;
   const int grid = min(total, sms);
-#define TC_DISPATCH(BN_)                                                                   \
-  if (BN == BN_) {                                                                         \
-    if (!a_mn && !b_mn) return launch_cfg<BN_, 0, 0>(ma, mb, md, p, grid, st);             \
-    if (!a_mn && b_mn) return launch_cfg<BN_, 0, 1>(ma, mb, md, p, grid, st);              \
-    return launch_cfg<BN_, 1, 1>(ma, mb, md, p, grid, st);                                 \
+  // epilogue specialisation: the combinations the model uses get their own instantiation, the rest run
+  // the generic (run-time flag) kernel
+  const int epi = (a->bias ? kEpiBias : 0) | (a->relu ? kEpiRelu : 0) | (a->relu_aux ? kEpiAux : 0) |
+                  (a->dropout_p > 0.f ? kEpiDrop : 0) | (a->residual ? kEpiRes : 0);
+#ifdef DGPT_GEMM_TS
+  {  // debug build: run synchronously and print the stamp deltas of the first three tiles of block 0
+    int rcx = (BN == 256) ? launch_cfg<256, 0, 0, kEpiBias | kEpiRelu>(ma, mb, md, p, grid, st)
+                          : launch_cfg<128, 0, 0, kEpiBias | kEpiRelu>(ma, mb, md, p, grid, st);
+    cudaStreamSynchronize(st);
+    long long h[3 * 64];
+    cudaMemcpy(h, p.ts, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int t = 0; t < 3; ++t) {
+      printf("tile %d:", t);
+      for (int i = 1; i < 48 && h[t * 64 + i]; ++i) printf(" %lld", h[t * 64 + i] - h[t * 64 + i - 1]);
+      printf("\n");
+    }
+    fflush(stdout);
+    return rcx;
   }
-  TC_DISPATCH(64)
+#endif
+#define TC_EPI(BN_, A_, B_, E_) \
+  if (epi == (E_)) return launch_cfg<BN_, A_, B_, (E_)>(ma, mb, md, p, grid, st);
+#define TC_DISPATCH(BN_)                                                          \
+  if (BN == BN_) {                                                                \
+    if (!a_mn && !b_mn) {                                                         \
+      TC_EPI(BN_, 0, 0, 0)                                                        \
+      TC_EPI(BN_, 0, 0, kEpiBias)                                                 \
+      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu)                                      \
+      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRes)                                       \
+      TC_EPI(BN_, 0, 0, kEpiBias | kEpiDrop | kEpiRes)                            \
+      return launch_cfg<BN_, 0, 0, -1>(ma, mb, md, p, grid, st);                  \
+    }                                                                             \
+    if (!a_mn && b_mn) {                                                          \
+      TC_EPI(BN_, 0, 1, 0)                                                        \
+      TC_EPI(BN_, 0, 1, kEpiAux)                                                  \
+      return launch_cfg<BN_, 0, 1, -1>(ma, mb, md, p, grid, st);                  \
+    }                                                                             \
+    TC_EPI(BN_, 1, 1, 0)                                                          \
+    return launch_cfg<BN_, 1, 1, -1>(ma, mb, md, p, grid, st);                    \
+  }
   TC_DISPATCH(128)
   TC_DISPATCH(256)
 #undef TC_DISPATCH
+#undef TC_EPI
   set_error("gemm_tc: no tile configuration for N=%d", a->N);
   return DGPT_E_ARG;
 }

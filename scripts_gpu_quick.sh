@@ -1,5 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py -q --timeout 300 2>&1 | tail -8
-timeout -k 10 600 python -m pytest tests/test_gpu_engine.py tests/test_gpu_models.py -q --timeout 500 2>&1 | tail -8
-timeout -k 10 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
+timeout -k 10 300 python -m pytest tests/test_gpu_kernels.py -q -k "tcgen05" --timeout 200 2>&1 | tail -4
+echo "--- normal"; python tools/gemm_probe.py 2>&1 | tail -5
+for d in 1 2; do echo "--- debug=$d"; DGPT_GEMM_DEBUG=$d python tools/gemm_probe.py ffn1_fwd qkv_fwd 2>&1 | tail -2; done

@@ -24,6 +24,7 @@ def launches(path):
 
 
 def stalls(rep, top=25):
+    top = int(top)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
