@@ -231,20 +231,60 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // backward
 // ===========================================================================
 static constexpr int kBwdThreads = 64 + 256;
-static constexpr int kBwdSmem = 8 * 16384 + 2 * 32768 + 2048 + 1024 + 128;
+static constexpr int kBwdSmem = 8 * 16384 + 2 * 32768 + 16384 + 2048 + 1024 + 128;
 
+// one 32-key chunk of one query row: P, dropout, dS -> swizzled bf16 rows of the Pd / dS tiles
+template <bool DIAG, bool DROP>
+__device__ __forceinline__ void bwd_chunk(const AttnTcP& p, uint32_t lane_addr_st, uint32_t lane_addr_dp, uint8_t* sPd,
+                                          uint8_t* sDs, int row, int k0, float sc, float lse2, float Dq, uint64_t seed,
+                                          uint64_t base) {
+  uint32_t st[32], dp[32];
+  tmem_ld32(lane_addr_st + k0, st);
+  tmem_ld32(lane_addr_dp + k0, dp);
+  tmem_ld_wait();
+  float pd[32], ds[32];
+#pragma unroll
+  for (int t4 = 0; t4 < 8; ++t4) {
+    uint32_t bw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+    if (DROP) {
+      const u32x4 bits = dropout_bits4(seed, p.site, (base + k0 + 4 * t4) >> 2);
+      bw[0] = bits.x; bw[1] = bits.y; bw[2] = bits.z; bw[3] = bits.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = 4 * t4 + u;
+      float pv = exp2f(__uint_as_float(st[t]) * sc - lse2);
+      if (DIAG) pv = (k0 + t) <= row ? pv : 0.f;
+      float dpv = __uint_as_float(dp[t]);
+      float pdv = pv;
+      if (DROP) {
+        const bool keep = bw[u] >= p.thr;
+        dpv = keep ? dpv * p.inv_keep : 0.f;
+        pdv = keep ? pv * p.inv_keep : 0.f;
+      }
+      pd[t] = pdv;
+      ds[t] = pv * (dpv - Dq) * p.scale;
+    }
+  }
+  store_row32_sw128(sPd, row, k0, pd);
+  store_row32_sw128(sDs, row, k0, ds);
+}
+
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do, AttnTcP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                   const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_dq,
+                   const __grid_constant__ CUtensorMap map_dk, const __grid_constant__ CUtensorMap map_dv, AttnTcP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                  // [2][128 x 64]
   uint8_t* sK = smem + 2 * 16384;
   uint8_t* sV = smem + 4 * 16384;
   uint8_t* sG = smem + 6 * 16384;      // dO
-  uint8_t* sPd = smem + 8 * 16384;     // Pd  [128 q x 128 kv] as two K-major 64-key blocks
+  uint8_t* sPd = smem + 8 * 16384;     // Pd  [128 q x 128 kv] as two K-major 64-key blocks (first: the O tiles)
   uint8_t* sDs = sPd + 32768;          // dS  (same layout)
-  float* lse_s = reinterpret_cast<float*>(sDs + 32768);  // [256]  lse * log2(e)
+  uint8_t* sSt = sDs + 32768;          // [128 x 64] bf16 staging tile for the dQ / dK / dV TMA stores
+  float* lse_s = reinterpret_cast<float*>(sSt + 16384);  // [256]  lse * log2(e)
   float* D_s = lse_s + 256;                              // [256]  rowsum(dO * O)
   uint64_t* bars = reinterpret_cast<uint64_t*>(D_s + 256);
   uint64_t *ld_full = bars, *st_full = bars + 1, *ps_full = bars + 2, *drained = bars + 3, *acc_done = bars + 4;
@@ -261,6 +301,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&map_do);
+    prefetch_tensormap(&map_o);
     mbar_init(ld_full, 1);
     mbar_init(st_full, 1);
     mbar_init(ps_full, 8);
@@ -277,12 +318,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(ld_full, 16384 * 4 * ntile);
+      mbar_expect_tx(ld_full, 16384 * 5 * ntile);
       for (int t = 0; t < ntile; ++t) {
+        tma_load_2d(sG + t * 16384, &map_do, ld_full, h * HD, row0 + t * QT);
+        tma_load_2d(sPd + t * 16384, &map_o, ld_full, h * HD, row0 + t * QT);  // O: only for D = rowsum(dO * O)
         tma_load_2d(sQ + t * 16384, &map_q, ld_full, h * HD, row0 + t * QT);
         tma_load_2d(sK + t * 16384, &map_k, ld_full, h * HD, row0 + t * QT);
         tma_load_2d(sV + t * 16384, &map_v, ld_full, h * HD, row0 + t * QT);
-        tma_load_2d(sG + t * 16384, &map_do, ld_full, h * HD, row0 + t * QT);
       }
     }
   } else if (warp == 1) {
@@ -337,20 +379,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // ------------------------------ 256 compute threads --------------------------------
     const int cw = warp - 2;            // 0..7
     const int quad = warp & 3;          // TMEM lane quadrant of this warp
-    const int half = cw >> 2;           // which 64 of the 128 key columns
-    const int kvl = quad * 32 + lane;   // accumulator row inside the tile (query row for S/dP/dQ, key row for dV/dK)
+    const int half = cw >> 2;           // which 64 of the 128 key columns (and of the 64 head dims when draining)
+    const int rowl = quad * 32 + lane;  // accumulator row inside the tile (query row for S/dP/dQ, key row for dV/dK)
     const int ct = threadIdx.x - 64;    // 0..255
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint64_t seed = p.seed;
-    if (p.thr && p.seed_dev) seed += *p.seed_dev;
-    // D_i = dO_i . O_i and lse_i * log2e for every query row of this (b, h)
+    if (DROP && p.seed_dev) seed += *p.seed_dev;
+    // D_i = dO_i . O_i for every query row, read back from the TMA-loaded (swizzled) tiles
+    mbar_wait(ld_full, 0);
     if (ct < p.T) {
-      const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (int64_t)(row0 + ct) * p.do_rs + h * HD);
-      const uint4* op = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o_in) + (int64_t)(row0 + ct) * p.o_rs + h * HD);
+      const int tl = ct >> 7, r = ct & 127;
+      const uint8_t* gr = sG + tl * 16384 + r * 128;
+      const uint8_t* orow = sPd + tl * 16384 + r * 128;
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint4 g = __ldg(gp + c), o = __ldg(op + c);
+        const int off = (c ^ (r & 7)) << 4;
+        const uint4 g = *reinterpret_cast<const uint4*>(gr + off), o = *reinterpret_cast<const uint4*>(orow + off);
         const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -363,15 +408,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       D_s[ct] = acc;
       lse_s[ct] = p.lse[((int64_t)b * p.NH + h) * p.T + ct] * kLog2e;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // D/lse visible; the O tiles may now be overwritten by Pd
     const float sc = p.scale * kLog2e;
+    int n_stores = 0;
 
-    auto drain = [&](uint32_t tm_col, void* dst, int64_t rs, int tile) {
-      // 128 x 64 fp32 accumulator -> bf16 rows; this thread owns 32 columns of one row
+    // 128 x 64 fp32 accumulator -> bf16 -> swizzled staging tile -> one TMA store
+    auto drain = [&](uint32_t tm_col, const CUtensorMap* map, int tile) {
       uint32_t r[32];
       tmem_ld32(lane_addr + tm_col + half * 32, r);
+      if (n_stores > 0) {  // the previous store must have finished reading the staging tile
+        if (ct == 0) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       tmem_ld_wait();
-      __nv_bfloat16* rowp = reinterpret_cast<__nv_bfloat16*>(dst) + (int64_t)(row0 + tile * QT + kvl) * rs + h * HD + half * 32;
+      uint8_t* rp = sSt + rowl * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 w;
@@ -379,8 +429,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         w.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
         w.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
         w.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-        *reinterpret_cast<uint4*>(rowp + 8 * j) = w;
+        *reinterpret_cast<uint4*>(rp + (((half * 4 + j) ^ (rowl & 7)) << 4)) = w;
       }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ct == 0) {
+        tma_store_2d(map, sSt, h * HD, row0 + tile * QT);
+        bulk_commit();
+      }
+      ++n_stores;
     };
 
     for (int pr = 0; pr < npair; ++pr) {
@@ -388,46 +445,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_wait(st_full, pr & 1);  // also implies the accumulate MMAs of the previous pair retired
       tc_fence_after();
       if (pr == 1) {               // (0,0) finished query tile 0
-        drain(TM_DQ, p.dq, p.dq_rs, 0);
+        drain(TM_DQ, &map_dq, 0);
       } else if (pr == 2) {        // (1,0) finished key tile 0
-        drain(TM_DV, p.dv, p.dv_rs, 0);
-        drain(TM_DK, p.dk, p.dk_rs, 0);
+        drain(TM_DV, &map_dv, 0);
+        drain(TM_DK, &map_dk, 0);
       }
       if (pr > 0) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(drained);
       }
-      const bool diag = (i == j);
-      const int qi = i * QT + kvl;  // this thread's query row (kvl = row inside the tile)
+      const int qi = i * QT + rowl;  // this thread's query row
       const float lse2 = lse_s[qi], Dq = D_s[qi];
       const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + (uint64_t)(j * QT);
+      if (i == j) {
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        const int k0 = half * 64 + c;  // first key column (inside the tile) of this chunk
-        uint32_t st[32], dp[32];
-        tmem_ld32(lane_addr + TM_ST + k0, st);
-        tmem_ld32(lane_addr + TM_DP + k0, dp);
-        tmem_ld_wait();
-        float pd[32], ds[32];
-#pragma unroll
-        for (int t4 = 0; t4 < 8; ++t4) {
-          u32x4 bits = u32x4{0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
-          if (p.thr) bits = dropout_bits4(seed, p.site, (base + k0 + 4 * t4) >> 2);
-          const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int t = 4 * t4 + u;
-            const bool valid = !diag || (k0 + t) <= kvl;
-            const float pv = valid ? exp2f(__uint_as_float(st[t]) * sc - lse2) : 0.f;
-            const bool keep = bw[u] >= p.thr;
-            const float dpv = keep ? __uint_as_float(dp[t]) * p.inv_keep : 0.f;
-            pd[t] = keep ? pv * p.inv_keep : 0.f;
-            ds[t] = pv * (dpv - Dq) * p.scale;
-          }
-        }
-        store_row32_sw128(sPd, kvl, k0, pd);
-        store_row32_sw128(sDs, kvl, k0, ds);
+        for (int c = 0; c < 64; c += 32)
+          bwd_chunk<true, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, sPd, sDs, rowl, half * 64 + c, sc, lse2, Dq, seed, base);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32)
+          bwd_chunk<false, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, sPd, sDs, rowl, half * 64 + c, sc, lse2, Dq, seed, base);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -437,9 +475,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int last = ntile - 1;
-    drain(TM_DV, p.dv, p.dv_rs, last);
-    drain(TM_DK, p.dk, p.dk_rs, last);
-    drain(TM_DQ, p.dq, p.dq_rs, last);
+    drain(TM_DV, &map_dv, last);
+    drain(TM_DK, &map_dk, last);
+    drain(TM_DQ, &map_dq, last);
+    if (ct == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -500,22 +539,29 @@ int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
 }
 
 int launch_attn_bwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
-  CUtensorMap mq, mk, mv, mg;
+  CUtensorMap mq, mk, mv, mg, mo, mdq, mdk, mdv;
   const int64_t rows = (int64_t)a->B * a->Tk, cols = (int64_t)a->NH * HD;
   int rc;
   if ((rc = make_tmap_bf16_2d(&mq, a->q, cols, rows, a->q_rs, QT))) return rc;
   if ((rc = make_tmap_bf16_2d(&mk, a->k, cols, rows, a->k_rs, QT))) return rc;
   if ((rc = make_tmap_bf16_2d(&mv, a->v, cols, rows, a->v_rs, QT))) return rc;
   if ((rc = make_tmap_bf16_2d(&mg, a->d_o, cols, rows, a->do_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mo, a->o, cols, rows, a->o_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mdq, a->dq, cols, rows, a->dq_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mdk, a->dk, cols, rows, a->dk_rs, QT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&mdv, a->dv, cols, rows, a->dv_rs, QT))) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
     if (e != cudaSuccess) { set_error("attn_bwd_tc: smem attribute: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
     attr = true;
   }
   AttnTcP p = make_tc_params(a);
   dim3 grid(a->NH, a->B);
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, p);
+  if (p.thr) attn_bwd_tc_kernel<true><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
+  else attn_bwd_tc_kernel<false><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
   return check_launch("attn_bwd_tc");
 }
 

@@ -72,6 +72,45 @@ __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __rest
   dpos[(int64_t)pos_offset * C + i] += acc;
 }
 
+// Fast token-gradient path when the whole [V, C] table fits in shared memory (80 x 384 fp32 = 120 KB):
+// every CTA owns a slice of the rows and a private table; thread c adds dx[m, c] into table[idx[m]][c]
+// (each thread touches only its own columns, so no atomics inside the CTA), then the rows of the
+// table that were hit are added to the global gradient with one red.add per element.
+__global__ void __launch_bounds__(512) embed_bwd_tok_smem_kernel(const int64_t* __restrict__ idx,
+                                                                 const float* __restrict__ dx,
+                                                                 float* __restrict__ dtok, int M, int C, int V,
+                                                                 int rows_per_cta) {
+  extern __shared__ float table[];  // [V][C] then hit flags [V]
+  int* hit = reinterpret_cast<int*>(table + (size_t)V * C);
+  for (int i = threadIdx.x; i < V * C; i += blockDim.x) table[i] = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) hit[i] = 0;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  for (int m = r0; m < r1; m += 4) {  // four rows in flight: the loop is bound by global-load latency
+    int v[4];
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = m + u < r1 ? (int)idx[m + u] : -1;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v[u] >= 0) hit[v[u]] = 1;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = v[u] >= 0 ? dx[(int64_t)(m + u) * C + c] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v[u] >= 0) table[v[u] * C + c] += x[u];
+    }
+  }
+  __syncthreads();
+  for (int v = 0; v < V; ++v) {
+    if (!hit[v]) continue;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dtok[(int64_t)v * C + c], table[v * C + c]);
+  }
+}
+
 // dtok[v, :] += sum_{m: idx[m]==v} dx[m, :]; one CTA per (v, 512-column chunk).
 // The 80-row table would serialise global atomics, so each CTA scans idx (256 entries per
 // step), builds an ORDERED list of matching rows in shared memory (deterministic sum order)
@@ -271,7 +310,7 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
 }
 
 template <int NV, typename DyT, typename MT>
-__global__ void __launch_bounds__(256) ln_bwd_fast_kernel(
+__global__ void __launch_bounds__(256, 4) ln_bwd_fast_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, MT* __restrict__ dxm,
@@ -612,8 +651,21 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
   if ((int64_t)B * T == 0) return DGPT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dpos) embed_bwd_pos_kernel<<<ceil_div((int64_t)T * C, 256), 256, 0, st>>>(dx, dpos, B, T, C, pos_offset);
-  dim3 grid(V, ceil_div(C, 512));
-  embed_bwd_tok_kernel<<<grid, 256, 0, st>>>(idx, dx, dtok, B * T, C);
+  const size_t table_bytes = ((size_t)V * C + V) * sizeof(float);
+  if (table_bytes <= 200 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(embed_bwd_tok_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    const int M = B * T;
+    const int ctas = min(kSMs, ceil_div(M, 32));
+    const int rows_per_cta = ceil_div(M, ctas);
+    embed_bwd_tok_smem_kernel<<<ceil_div(M, rows_per_cta), 512, table_bytes, st>>>(idx, dx, dtok, M, C, V, rows_per_cta);
+  } else {
+    dim3 grid(V, ceil_div(C, 512));
+    embed_bwd_tok_kernel<<<grid, 256, 0, st>>>(idx, dx, dtok, B * T, C);
+  }
   return check_launch("embed_bwd");
 }
 
@@ -647,7 +699,7 @@ int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma
   const bool fast = (C % 4 == 0) && C <= 1024 && al(x, 16) && al(gamma, 16) && al(dx, 16) && (!dres || al(dres, 16)) &&
                     al(dy, dy_dtype == DGPT_F32 ? 16 : 8) && (!dxm || al(dxm, dxm_dtype == DGPT_F32 ? 16 : 8));
   if (fast) {
-    const int grid = min(ceil_div(M, 8), kSMs * 2);
+    const int grid = min(ceil_div(M, 8), kSMs * 4);  // 4 CTAs (32 warps) per SM: the row loop is latency-bound
     const size_t smem = 8 * (size_t)C * sizeof(float);
     const int nv = ceil_div(C, 128);
 #define LN_FAST(NV, DyT, MT)                                                                                   \

@@ -326,7 +326,7 @@ class Runner:
         self._gemm(dh, xn2, self.g(L["ffn"][1]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                    split_k=self._splits(F, C, M, sm))
         ops.raw_colsum(dh, self.g(L["ffn"][2]), accumulate=True)
-        dxn = self.buf("dxn", (M, C), torch.float32)
+        dxn = self.buf("dxn", (M, C))  # activation dtype: bf16 in tensor mode halves this round trip
         self._gemm(dh, self.w(L["ffn"][1]), dxn, b_major=MAJOR_MN)
         # ---- LN2 backward + residual-gradient add + masked copy for the proj GEMMs ----
         g1 = g_other

@@ -1,4 +1,4 @@
 #!/bin/bash
-timeout -k 10 300 python -m pytest tests/test_gpu_kernels.py -q -k "tcgen05" --timeout 200 2>&1 | tail -4
-echo "--- normal"; python tools/gemm_probe.py 2>&1 | tail -5
-for d in 1 2; do echo "--- debug=$d"; DGPT_GEMM_DEBUG=$d python tools/gemm_probe.py ffn1_fwd qkv_fwd 2>&1 | tail -2; done
+python tools/graph_overhead.py 2>&1 | tail -1
+timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_engine.py -q --timeout 500 2>&1 | tail -4
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
