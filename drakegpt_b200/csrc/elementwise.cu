@@ -4,6 +4,7 @@
 // on-device sampler.  All are grid-sized in multiples of the SM count or one
 // warp per row with float4 accesses; none allocates or synchronises.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dgpt {
 
@@ -310,7 +311,7 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
 }
 
 template <int NV, typename DyT, typename MT>
-__global__ void __launch_bounds__(256, 4) ln_bwd_fast_kernel(
+__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, MT* __restrict__ dxm,
@@ -331,14 +332,22 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_fast_kernel(
   for (int row = blockIdx.x * 8 + w; row < M; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
     const int64_t ro = (int64_t)row * C;
-    float4 d[NV], xh[NV];
+    float4 d[NV], xh[NV], rr[NV];
     float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {  // all three input streams in flight together
+      const int q = lane + 32 * i;
+      if (q < nv) {
+        d[i] = ld4(dy + ro + 4 * q);
+        xh[i] = ld4(x + ro + 4 * q);
+        rr[i] = dres ? ld4(dres + ro + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int q = lane + 32 * i;
       if (q < nv) {
-        d[i] = ld4(dy + ro + 4 * q);
-        const float4 xv = ld4(x + ro + 4 * q);
+        const float4 xv = xh[i];
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         const float4 t = make_float4(d[i].x * g[i].x, d[i].y * g[i].y, d[i].z * g[i].z, d[i].w * g[i].w);
         s1 += (t.x + t.y) + (t.z + t.w);
@@ -355,10 +364,7 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_fast_kernel(
       if (q < nv) {
         float4 v = make_float4(rs * (d[i].x * g[i].x - s1 - xh[i].x * s2), rs * (d[i].y * g[i].y - s1 - xh[i].y * s2),
                                rs * (d[i].z * g[i].z - s1 - xh[i].z * s2), rs * (d[i].w * g[i].w - s1 - xh[i].w * s2));
-        if (dres) {
-          const float4 r = ld4(dres + ro + 4 * q);
-          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-        }
+        v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
         st4(dx + ro + 4 * q, v);
         if (dxm) {
           if (thr) {
@@ -391,6 +397,154 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_fast_kernel(
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += sm[k * C + c];
       atomicAdd(&out[c], s);
+    }
+  }
+}
+
+// Streaming version of the same math for the training shapes: a producer thread keeps a 4-deep ring of
+// 8-row blocks (dy, x, dres, mean, rstd) in flight with cp.async.bulk + mbarriers, eight consumer warps
+// take one row each out of shared memory.  Bytes in flight no longer depend on occupancy / registers
+// (the register version stalled at ~35 % of HBM bandwidth with 16 resident warps per SM); one CTA per SM.
+static constexpr int kLnRows = 8;     // rows per stage = consumer warps
+static constexpr int kLnStages = 4;
+
+template <int NV, typename DyT, typename MT>
+__global__ void __launch_bounds__(32 + 32 * kLnRows, 1) ln_bwd_stream_kernel(
+    const DyT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, MT* __restrict__ dxm,
+    float* __restrict__ dxm_colsum, uint32_t thr, float inv_keep, uint64_t seed,
+    const uint64_t* __restrict__ seed_dev, uint32_t site, int M, int C) {
+  extern __shared__ __align__(128) uint8_t lsm[];
+  using namespace ptx;
+  const int dy_row = C * (int)sizeof(DyT), f_row = C * 4;
+  const int stage_bytes = kLnRows * (dy_row + 2 * f_row) + 2 * kLnRows * 4 + 64;  // + mean, rstd (padded)
+  const int stage_stride = (stage_bytes + 127) & ~127;
+  uint64_t* full = reinterpret_cast<uint64_t*>(lsm + (size_t)kLnStages * stage_stride);
+  uint64_t* empty = full + kLnStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLnStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kLnRows);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int nblocks = (M + kLnRows - 1) / kLnRows;
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int r0 = blk * kLnRows;
+        const int nr = min(kLnRows, M - r0);
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = lsm + (size_t)s * stage_stride;
+        const uint32_t bytes = nr * (dy_row + f_row + (dres ? f_row : 0)) + 2 * kLnRows * 4;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_load_1d(st, dy + (int64_t)r0 * C, nr * dy_row, &full[s]);
+        bulk_load_1d(st + kLnRows * dy_row, x + (int64_t)r0 * C, nr * f_row, &full[s]);
+        if (dres) bulk_load_1d(st + kLnRows * (dy_row + f_row), dres + (int64_t)r0 * C, nr * f_row, &full[s]);
+        // mean / rstd: always a full 32-byte copy (the arrays are padded by the caller's allocation granularity;
+        // rows >= M are never consumed)
+        bulk_load_1d(st + kLnRows * (dy_row + 2 * f_row), mean + r0, kLnRows * 4, &full[s]);
+        bulk_load_1d(st + kLnRows * (dy_row + 2 * f_row) + kLnRows * 4, rstd + r0, kLnRows * 4, &full[s]);
+        if (++s == kLnStages) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  // ------------------------------- consumers --------------------------------
+  if (thr && seed_dev) seed += *seed_dev;
+  const int cw = warp - 1;  // row inside the block
+  const int nv = C >> 2;
+  float4 g[NV], ag[NV], ab[NV], am[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int q = lane + 32 * i;
+    g[i] = q < nv ? ld4(gamma + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = ab[i] = am[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.f / (float)C;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int row = blk * kLnRows + cw;
+    mbar_wait(&full[s], ph);
+    const uint8_t* st = lsm + (size_t)s * stage_stride;
+    if (row < M) {
+      const DyT* sdy = reinterpret_cast<const DyT*>(st) + cw * C;
+      const float* sx = reinterpret_cast<const float*>(st + kLnRows * dy_row) + cw * C;
+      const float* sr = reinterpret_cast<const float*>(st + kLnRows * (dy_row + f_row)) + cw * C;
+      const float* sms = reinterpret_cast<const float*>(st + kLnRows * (dy_row + 2 * f_row));
+      const float mu = sms[cw], rs = sms[kLnRows + cw];
+      const int64_t ro = (int64_t)row * C;
+      float4 d[NV], xh[NV];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nv) {
+          d[i] = ld4(sdy + 4 * q);
+          const float4 xv = ld4(sx + 4 * q);
+          xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+          const float4 t = make_float4(d[i].x * g[i].x, d[i].y * g[i].y, d[i].z * g[i].z, d[i].w * g[i].w);
+          s1 += (t.x + t.y) + (t.z + t.w);
+          s2 += (t.x * xh[i].x + t.y * xh[i].y) + (t.z * xh[i].z + t.w * xh[i].w);
+          ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+          ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+        }
+      }
+      s1 = warp_sum(s1) * invC;
+      s2 = warp_sum(s2) * invC;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nv) {
+          float4 v = make_float4(rs * (d[i].x * g[i].x - s1 - xh[i].x * s2), rs * (d[i].y * g[i].y - s1 - xh[i].y * s2),
+                                 rs * (d[i].z * g[i].z - s1 - xh[i].z * s2), rs * (d[i].w * g[i].w - s1 - xh[i].w * s2));
+          if (dres) {
+            const float4 r = ld4(sr + 4 * q);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+          }
+          st4(dx + ro + 4 * q, v);
+          if (dxm) {
+            if (thr) {
+              const u32x4 b = dropout_bits4(seed, site, (uint64_t)row * (uint64_t)nv + (uint64_t)q);
+              v.x = b.x >= thr ? v.x * inv_keep : 0.f;
+              v.y = b.y >= thr ? v.y * inv_keep : 0.f;
+              v.z = b.z >= thr ? v.z * inv_keep : 0.f;
+              v.w = b.w >= thr ? v.w * inv_keep : 0.f;
+            }
+            st4(dxm + ro + 4 * q, v);
+            am[i].x += v.x; am[i].y += v.y; am[i].z += v.z; am[i].w += v.w;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == kLnStages) { s = 0; ph ^= 1; }
+  }
+  // cross-warp reduction of the three column accumulators through the (now idle) stage memory
+  float* red = reinterpret_cast<float*>(lsm);
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    float* out = which == 0 ? dgamma : which == 1 ? dbeta : dxm_colsum;
+    if (out == nullptr) continue;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nv) st4(red + cw * C + 4 * q, which == 0 ? ag[i] : which == 1 ? ab[i] : am[i]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int c = threadIdx.x - 32; c < C; c += 256) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kLnRows; ++k) sacc += red[k * C + c];
+      atomicAdd(&out[c], sacc);
     }
   }
 }
@@ -698,8 +852,45 @@ int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma
   auto al = [](const void* q, uintptr_t a) { return ((uintptr_t)q & (a - 1)) == 0; };
   const bool fast = (C % 4 == 0) && C <= 1024 && al(x, 16) && al(gamma, 16) && al(dx, 16) && (!dres || al(dres, 16)) &&
                     al(dy, dy_dtype == DGPT_F32 ? 16 : 8) && (!dxm || al(dxm, dxm_dtype == DGPT_F32 ? 16 : 8));
+  const bool stream_ok = fast && M >= 1024 && (C * (dy_dtype == DGPT_F32 ? 4 : 2)) % 16 == 0 && al(mean, 16) &&
+                         al(rstd, 16) && al(dy, 16) && M % kLnRows == 0;
+  if (stream_ok) {
+    const int dyb = dy_dtype == DGPT_F32 ? 4 : 2;
+    const int stage_bytes = kLnRows * (C * dyb + 2 * C * 4) + 2 * kLnRows * 4 + 64;
+    const size_t smem = (size_t)kLnStages * ((stage_bytes + 127) & ~127) + 2 * kLnStages * 8 + 64;
+    const int nv = ceil_div(C, 128);
+    const int grid = min(ceil_div(M, kLnRows), kSMs);
+#define LN_STREAM(NV, DyT, MT)                                                                                       \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(ln_bwd_stream_kernel<NV, DyT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    ln_bwd_stream_kernel<NV, DyT, MT><<<grid, 32 + 32 * kLnRows, smem, st>>>(                                        \
+        (const DyT*)dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (MT*)dxm, dxm_colsum, thr, ik, seed, seed_dev, \
+        site, M, C);                                                                                                 \
+  } while (0)
+#define LN_STREAM_T(NV)                                                                \
+  do {                                                                                 \
+    if (dy_dtype == DGPT_F32 && dxm_dtype == DGPT_F32) LN_STREAM(NV, float, float);    \
+    else if (dy_dtype == DGPT_F32) LN_STREAM(NV, float, __nv_bfloat16);                \
+    else if (dxm_dtype == DGPT_F32) LN_STREAM(NV, __nv_bfloat16, float);               \
+    else LN_STREAM(NV, __nv_bfloat16, __nv_bfloat16);                                  \
+  } while (0)
+    if (smem <= 200 * 1024) {
+      if (nv <= 1) LN_STREAM_T(1);
+      else if (nv == 2) LN_STREAM_T(2);
+      else if (nv == 3) LN_STREAM_T(3);
+      else if (nv == 4) LN_STREAM_T(4);
+      else LN_STREAM_T(8);
+      return check_launch("ln_bwd_stream");
+    }
+#undef LN_STREAM_T
+#undef LN_STREAM
+  }
   if (fast) {
-    const int grid = min(ceil_div(M, 8), kSMs * 4);  // 4 CTAs (32 warps) per SM: the row loop is latency-bound
+    const int grid = min(ceil_div(M, 8), kSMs * 2);
     const size_t smem = 8 * (size_t)C * sizeof(float);
     const int nv = ceil_div(C, 128);
 #define LN_FAST(NV, DyT, MT)                                                                                   \
