@@ -50,7 +50,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -159,7 +159,10 @@ def time_gemm_roofline(dev, pk):
     t = statistics.mean(times)
     tf = 2.0 * M * N * K / t / 1e12
     return {"bound": "tensor", "achieved": tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": tf / pk["bf16_burst"],
-            "traffic": None, "kernel": "gemm_tc_kernel<256,0,0> FFN1 16384x1536x384 +bias+ReLU, L2 flushed",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/r1_gemm_ffn1_metrics.txt
+            # (13.80 MB + 0.77 MB: inputs only, the 50 MB bf16 output stays in the 126 MB L2)
+            "traffic": 14.57e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * N),
+            "kernel": "gemm_tc_kernel<256,0,0,bias|relu> FFN1 16384x1536x384 +bias+ReLU, L2 flushed",
             "peak_source": pk["src"] + " burst", "us_per_launch": t * 1e6}
 
 
@@ -259,7 +262,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])

@@ -1,4 +1,3 @@
 #!/bin/bash
-python tools/ln_probe.py 2>&1 | tail -4
-timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_engine.py -q --timeout 500 -x 2>&1 | tail -4
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
+timeout -k 10 900 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -4
+python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_r1.json; cut -c1-250 gpurun_out/bench_r1.json
