@@ -80,7 +80,7 @@ def _declare(lib):
         "dgpt_cross_entropy": [vp, i32, vp, vp, vp, i32, i32, vp, i32, i32, vp],
         "dgpt_adamw": [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp],
         "dgpt_counter_add": [vp, u64, vp],
-        "dgpt_sample": [vp, i32, vp, i64, i32, i32, i32, i32, u64, u32, vp],
+        "dgpt_sample": [vp, i32, vp, i64, i32, i32, i32, i32, u64, vp, u32, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -446,40 +446,77 @@ class Runner:
         return x
 
     @torch.no_grad()
-    def generate(self, idx, max_new_tokens, greedy=False, seed=None):
-        """(B,t0) int64 -> (B,t0+N) int64.  Sampling (softmax -> multinomial, or argmax) runs on the device."""
+    def generate(self, idx, max_new_tokens, greedy=False, seed=None, use_graphs=None):
+        """(B,t0) int64 -> (B,t0+N) int64.  Sampling (softmax -> multinomial, or argmax) runs on the device.
+
+        While the window has not slid (t < context_length) every position is one KV-cached decode step;
+        with ``use_graphs`` (default: tensor mode) each (batch, position) step is captured once in a CUDA
+        graph -- the sequence buffer, KV caches and sampling seed live in device memory -- and later calls
+        replay it, which removes the ~50 host-side kernel launches per token.
+        """
         self._reattach()
         self.flat.refresh_shadow()
         sp = self.spec
         Bn, t0 = idx.shape
         total = t0 + max_new_tokens
         seed = ops.next_seed() if seed is None else int(seed)
-        seq = torch.empty((total, Bn), device=self.device, dtype=torch.int64)  # time-major
-        seq[:t0].copy_(idx.t())
         tok = self.f(sp["tok"])
         V = tok.shape[0]
         if sp["kind"] == "BigramLM":
+            seq = torch.empty((total, Bn), device=self.device, dtype=torch.int64)  # time-major
+            seq[:t0].copy_(idx.t())
             logits = self.buf("d.logits", (Bn, V), torch.float32)
             for t in range(t0 - 1, total - 1):
                 ops.raw_embed_fwd(seq[t].view(Bn, 1), tok, None, logits.view(Bn, 1, V))
                 ops.raw_sample(logits, seq[t + 1], 0, greedy, seed, t)
             return seq.t().contiguous()
         ctx = sp["ctx"]
+        if use_graphs is None:
+            use_graphs = self.mode == "bf16"
+        # the in-window part of the sequence lives in a persistent buffer so captured graphs stay valid
+        win_len = min(total, ctx + 1)
+        seqw = self.buf("d.seq", (ctx + 1, Bn), torch.int64)
+        seq = seqw if total <= ctx + 1 else torch.empty((total, Bn), device=self.device, dtype=torch.int64)
+        seq[:t0].copy_(idx.t())
+        if seq is not seqw:
+            seqw[:min(t0, ctx + 1)].copy_(seq[:min(t0, ctx + 1)])
         caches = [self.buf(f"d.cache{li}", (ctx, Bn, 3 * L["NH"] * L["H"])) for li, L in enumerate(sp["layers"])]
         logits = self.buf("d.logits", (Bn, V), torch.float32)
-        for t in range(total - 1):
-            sampling = t >= t0 - 1
-            if t < ctx:
-                x = self._decode_token(seq[t], t, caches)
-                if not sampling:
-                    continue
+        sample_seed = self.buf("d.seed", (1,), torch.int64)
+        sample_seed.fill_(seed)
+        graphs = self.__dict__.setdefault("_decode_graphs", {})
+
+        def step_kernels(t, sampling, greedy_flag):
+            x = self._decode_token(seqw[t], t, caches)
+            if sampling:
                 xin = x if x.dtype == self.at else ops.raw_dropout_scale(x, self.buf("d.xl", x.shape))
                 self._gemm(xin, self.w(sp["lm"][0]), logits, bias=self.f(sp["lm"][1]))
-                ops.raw_sample(logits, seq[t + 1], 0, greedy, seed, t)
-            elif sampling:
-                # window slid: absolute positions of every token change -> recompute the window
+                ops.raw_sample(logits, seqw[t + 1], 0, greedy_flag, 0, t, seed_dev=sample_seed)
+
+        for t in range(min(total - 1, ctx)):
+            sampling = t >= t0 - 1
+            if not use_graphs:
+                step_kernels(t, sampling, greedy)
+                continue
+            key = (Bn, t, sampling, bool(greedy), id(self.flat))
+            g = graphs.get(key)
+            if g is None:
+                step_kernels(t, sampling, greedy)  # warm-up: allocates workspaces, loads kernels
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_kernels(t, sampling, greedy)
+                graphs[key] = g
+            else:
+                g.replay()
+        if seq is not seqw:
+            seq[:win_len].copy_(seqw[:win_len])
+        for t in range(ctx, total - 1):
+            if t >= t0 - 1:
+                # window slid: absolute positions of every token change -> recompute the window (reference
+                # semantics, src/model.py:625: idx[:, -context_length:])
                 win = seq[t - ctx + 1: t + 1].t().contiguous()
                 full, _ = self.forward(win)
                 last = full.view(Bn, ctx, V)[:, -1, :]
                 ops.raw_sample(last, seq[t + 1], 0, greedy, seed, t)
-        return seq.t().contiguous()
+        return seq[:total].t().contiguous()

@@ -205,10 +205,10 @@ def raw_counter_add(ctr, delta=1):
     check(_lib.lib().dgpt_counter_add(_p(ctr), int(delta), _stream()), "dgpt_counter_add")
 
 
-def raw_sample(logits, seq, pos, greedy, seed, step):
+def raw_sample(logits, seq, pos, greedy, seed, step, seed_dev=None):
     Bn, V = logits.shape
     check(_lib.lib().dgpt_sample(_p(logits), logits.stride(0), _p(seq), seq.stride(0), pos, Bn, V, int(greedy),
-                                 int(seed), int(step), _stream()), "dgpt_sample")
+                                 int(seed), _p(seed_dev), int(step), _stream()), "dgpt_sample")
 
 
 # --------------------------------------------------------------------------- #

@@ -213,11 +213,11 @@ int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream);
  * `logits[:, -1, :] -> F.softmax -> torch.multinomial -> torch.cat`,
  * src/model.py:628-635.  logits: row b at logits + b*ld ([V] fp32).
  *   greedy != 0: argmax (lowest index wins ties, like torch.argmax)
- *   else inverse-CDF sample with u = philox(seed, step, b).
+ *   else inverse-CDF sample with u = philox(seed + *seed_dev, step, b)  (seed_dev may be NULL).
  * Writes the token to seq[b*seq_ld + pos] (int64).
  * ------------------------------------------------------------------------- */
 int dgpt_sample(const float* logits, int ld, int64_t* seq, int64_t seq_ld, int pos, int B, int V,
-                int greedy, uint64_t seed, uint32_t step, void* stream);
+                int greedy, uint64_t seed, const uint64_t* seed_dev, uint32_t step, void* stream);
 
 #ifdef __cplusplus
 }
