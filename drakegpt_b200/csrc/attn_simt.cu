@@ -189,6 +189,69 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_simt_kernel(AttnP p) {
   }
 }
 
+// KV-cached decode step (Tq == 1, no dropout): one warp per (batch, head) streams that head's K and V
+// rows straight from the cache (each row is one contiguous 2*H- or 4*H-byte segment), scores and
+// probabilities stay in shared memory, nothing is staged through a per-CTA copy of the whole cache.
+// HBM-bound: 2 * Tk * H elements read per (b, h).
+static constexpr int kDecWarps = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(AttnP p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bh = blockIdx.x * kDecWarps + w;
+  if (bh >= p.B * p.NH) return;
+  const int b = bh / p.NH, h = bh % p.NH, H = p.H, Tk = p.Tk;
+  float* qs = smem + w * (H + Tk);  // [H] query, then [Tk] scores / probabilities
+  float* ps = qs + H;
+  const T* qr = (const T*)p.q + b * p.q_bs + h * H;  // the single query row (t = 0 of the q view)
+  for (int d = lane; d < H; d += 32) qs[d] = to_f32(qr[d]) * p.scale;
+  __syncwarp();
+  const T* kb = (const T*)p.k + b * p.k_bs + h * H;
+  const T* vb = (const T*)p.v + b * p.v_bs + h * H;
+  float mx = -INFINITY;
+  for (int j = lane; j < Tk; j += 32) {
+    const T* kr = kb + j * p.k_rs;
+    float sacc = 0.f;
+    if constexpr (sizeof(T) == 2) {
+      if ((H & 7) == 0) {
+        for (int d = 0; d < H; d += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(kr + d);
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[t]));
+            sacc = fmaf(qs[d + 2 * t], f.x, sacc);
+            sacc = fmaf(qs[d + 2 * t + 1], f.y, sacc);
+          }
+        }
+      } else {
+        for (int d = 0; d < H; ++d) sacc = fmaf(qs[d], to_f32(kr[d]), sacc);
+      }
+    } else {
+      for (int d = 0; d < H; ++d) sacc = fmaf(qs[d], to_f32(kr[d]), sacc);
+    }
+    ps[j] = sacc;
+    mx = fmaxf(mx, sacc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < Tk; j += 32) {
+    const float e = expf(ps[j] - mx);
+    ps[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  T* orow = (T*)p.o + b * p.o_bs + h * H;
+  for (int d = lane; d < H; d += 32) {  // lanes walk the head dimension: each V row is read coalesced
+    float acc = 0.f;
+    for (int j = 0; j < Tk; ++j) acc = fmaf(ps[j], to_f32(vb[j * p.v_rs + d]), acc);
+    orow[d] = from_f32<T>(acc * inv);
+  }
+}
+
 static AttnP make_params(const dgpt_attn_args* a) {
   AttnP p;
   p.q = a->q; p.k = a->k; p.v = a->v; p.d_o = a->d_o; p.o = a->o;
@@ -206,6 +269,15 @@ static AttnP make_params(const dgpt_attn_args* a) {
 static constexpr size_t kMaxSmem = 227 * 1024;
 
 int launch_attn_fwd_simt(const dgpt_attn_args* a, cudaStream_t st) {
+  if (a->Tq == 1 && a->dropout_p == 0.f && a->lse == nullptr) {  // KV-cached decode step
+    AttnP p = make_params(a);
+    const size_t smem = (size_t)kDecWarps * (a->H + a->Tk) * sizeof(float);
+    DGPT_REQUIRE(smem <= 48 * 1024, "attn_fwd(decode): Tk=%d H=%d needs %zu B of shared memory", a->Tk, a->H, smem);
+    const int grid = ceil_div((int64_t)a->B * a->NH, kDecWarps);
+    if (a->dtype == DGPT_F32) attn_decode_kernel<float><<<grid, kDecWarps * 32, smem, st>>>(p);
+    else attn_decode_kernel<__nv_bfloat16><<<grid, kDecWarps * 32, smem, st>>>(p);
+    return check_launch("attn_decode");
+  }
   const size_t smem = ((size_t)a->Tk * (a->H + 1) + (size_t)a->Tk * a->H + kWarps * a->H +
                        (size_t)kWarps * a->Tk) * sizeof(float);
   DGPT_REQUIRE(smem <= kMaxSmem, "attn_fwd(exact): Tk=%d H=%d needs %zu B of shared memory (max %zu)",
