@@ -15,7 +15,7 @@ MAJOR_K, MAJOR_MN = 0, 1
 
 EXPORTS = [
     "dgpt_last_error", "dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count",
-    "dgpt_dropout_keep_host", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
+    "dgpt_dropout_keep_host", "dgpt_gemm_set_cta_group", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
     "dgpt_embed_bwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
     "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
 ]
@@ -64,6 +64,8 @@ def _declare(lib):
     for name in ("dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count"):
         getattr(lib, name).restype = i32
         getattr(lib, name).argtypes = []
+    lib.dgpt_gemm_set_cta_group.restype = i32
+    lib.dgpt_gemm_set_cta_group.argtypes = [i32]
     lib.dgpt_dropout_keep_host.restype = i32
     lib.dgpt_dropout_keep_host.argtypes = [u64, u32, u64, f32]
     sig = {

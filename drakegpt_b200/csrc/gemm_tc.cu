@@ -39,6 +39,7 @@ struct TcParams {
   int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
   int vec_ok;      // epilogue operands (bias / residual / relu_aux) allow 16-byte loads
   int store_mode;  // StoreMode for D
+  int cta_group;   // 1, or 2 = CTA pairs (cluster of 2) sharing each MMA
 #ifdef DGPT_GEMM_TS
   long long* ts;   // cycle stamps of (block 0, first epilogue warp, lane 0) for the first tiles (debug builds)
 #endif
@@ -46,9 +47,15 @@ struct TcParams {
   Epilogue ep;
 };
 
-template <int BN>
+// CG = CTAs sharing one MMA (tcgen05 cta_group).  With CG = 2 a pair of CTAs computes a 256 x BN tile: each CTA
+// stages its own 128 rows of A but only HALF of B (the MMA reads the other half from the peer's shared
+// memory), so every SM ingests and re-reads a third (BN = 256) or a quarter (BN = 128) fewer operand
+// bytes per MMA cycle -- operand delivery (L2 -> SM ~43 B/cycle/SM measured) and shared-memory bandwidth
+// are what bound the single-CTA mainloop.
+template <int BN, int CG = 1>
 struct TcCfg {
-  static constexpr int kStageBytes = TBM * TBK * 2 + BN * TBK * 2;
+  static constexpr int kBBytes = (BN / CG) * TBK * 2;
+  static constexpr int kStageBytes = TBM * TBK * 2 + kBBytes;
   static constexpr int kStages = kStageBudget / kStageBytes > 8 ? 8 : kStageBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
   static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
@@ -202,15 +209,15 @@ __device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int 
 // --------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = TBM * TBK * 2;
-  constexpr int kBBytes = BN * TBK * 2;
-  constexpr uint32_t kIdesc = make_idesc_bf16(TBM, BN, A_MN, B_MN);
+  constexpr int kBBytes = Cfg::kBBytes;
+  constexpr uint32_t kIdesc = make_idesc_bf16(TBM * CG, BN, A_MN, B_MN);
 
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* stage_base = smem;
@@ -234,34 +241,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8 * CG);  // one arrive per epilogue warp of every CTA sharing the accumulator
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (CG == 2) {  // both CTAs of the pair have initialised their barriers before the paired TMEM allocation
+    __syncthreads();
+    cluster_sync_all();
+  }
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's TMEM and barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
+  // tile walk: with CG = 2 the pair handles pair-tiles (256 rows) and CTA rank r takes rows [128 r, 128 r + 128)
+  const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int tiles_mn = (p.m_tiles / CG) * p.n_tiles;
   const int total_tiles = tiles_mn * p.split_k;
+  const int t_first = blockIdx.x / CG, t_step = gridDim.x / CG;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ---------------------------
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-        const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
+        const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
           const int k0 = kb * TBK;
+          if (CG == 2) {
+            // both CTAs load into their own shared memory; all bytes are credited to the LEADER's barrier,
+            // which the leader arms for the pair's total
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * (kABytes + kBBytes));
+            const uint32_t lbar = mapa_u32(&full_bar[s], 0);
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < TBM / 64; ++c) tma_load_2d_2sm(sa + c * 8192, &map_a, lbar, m0 + c * 64, k0);
+            } else {
+              tma_load_2d_2sm(sa, &map_a, lbar, k0, m0);
+            }
+            const int nh = n0 + crank * (BN / 2);  // this CTA's half of the B tile
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c) tma_load_2d_2sm(sb + c * 8192, &map_b, lbar, nh + c * 64, k0);
+            } else {
+              tma_load_2d_2sm(sb, &map_b, lbar, k0, nh);
+            }
+            if (++s == kStages) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < TBM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
@@ -280,12 +319,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer -----------------------------
-    if (lane == 0) {
+    if (lane == 0 && crank == 0) {  // with CG = 2 only the pair's leader issues MMAs
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int ks = t / tiles_mn;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
@@ -304,12 +343,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                      : make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                      : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 1) tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
+          if (CG == 1) tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
+          else tc_commit_2sm(&empty_bar[s]);      // ... in both CTAs of the pair
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (CG == 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        else tc_commit_2sm(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -331,9 +373,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     epilogue_resolve_seed(ep);
     const bool bf16_out = ep.d_dtype == DGPT_BF16;
     const int mode = p.store_mode;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-      const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
       ep.first_split = (ks == 0);
       const int mrow0 = (p.debug & 1) ? p.M : m0 + quad * 32;  // debug bit 0: skip all epilogue work
       const int m = mrow0 + lane;
@@ -351,8 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint4 pre[8];
       if (p.vec_ok && row_ok && nbeg + 32 <= p.N) epilogue_prefetch<EPI>(ep, m, nbeg, pre);
 #ifdef DGPT_GEMM_TS
-      const bool stamp = p.ts && blockIdx.x == 0 && warp == 2 && lane == 0 && t < 3 * (int)gridDim.x;
-      long long* tsp = p.ts + (t / gridDim.x) * 64;
+      const bool stamp = p.ts && blockIdx.x == 0 && warp == 2 && lane == 0 && t < 3 * t_step;
+      long long* tsp = p.ts + (t / t_step) * 64;
       int tsi = 0;
 #define TS_MARK() do { if (stamp) tsp[tsi++] = clock64(); } while (0)
 #else
@@ -436,7 +478,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));  // the leader's MMA thread waits for both CTAs
+      }
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
     if (lane == 0) bulk_wait<0>();  // all output tiles have landed before the CTA retires
@@ -444,9 +489,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / retire while the pair's MMAs or arrives are in flight
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -504,22 +551,56 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI>
-static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const TcParams& p, int grid,
+template <int BN, int A_MN, int B_MN, int EPI, int CG>
+static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const TcParams& p, int grid,
                       cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%zu B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return DGPT_E_LAUNCH;
     }
     attr_done = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, md, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc: launch: %s", cudaGetErrorString(e));
+    return DGPT_E_LAUNCH;
+  }
   return check_launch("gemm_tc");
+}
+
+// Pair tiles (cta_group::2) are opt-in (dgpt_gemm_set_cta_group): on the model's shapes they measured no faster
+// than single-CTA tiles -- the 20-30 us GEMMs are bound by fixed per-launch / per-tile latencies and the
+// epilogue, not by operand delivery -- so the default stays 1.
+static int g_cta_group = 1;
+void set_gemm_cta_group(int g) { g_cta_group = (g == 2) ? 2 : 1; }
+
+// pair tiles whenever requested and the row-tile count is even, single-CTA tiles otherwise
+template <int BN, int A_MN, int B_MN, int EPI>
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb_half, const CUtensorMap& md,
+                      const TcParams& p, int sms, cudaStream_t st) {
+  if (p.cta_group == 2) {
+    const int total = (p.m_tiles / 2) * p.n_tiles * p.split_k;
+    return launch_one<BN, A_MN, B_MN, EPI, 2>(ma, mb_half, md, p, 2 * min(total, sms / 2), st);
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  return launch_one<BN, A_MN, B_MN, EPI, 1>(ma, mb, md, p, min(total, sms), st);
 }
 
 int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
@@ -530,9 +611,11 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   int sms = dgpt_sm_count();
   if (sms <= 0) sms = 148;
   const int m_tiles = ceil_div(a->M, TBM);
+  // 128 x 256 tiles ingest 25 % fewer operand bytes per MMA cycle than 128 x 128; a ragged last column
+  // tile (N = 1152 -> 4.5 tiles) costs less than that as soon as N >= 1024 (TMA zero-fills, the store clips)
   int BN = 256;
-  if (a->N <= 128 || a->N % 256 != 0) BN = 128;
-  if (BN == 256 && m_tiles * (a->N / 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
+  if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024)) BN = 128;
+  if (BN == 256 && m_tiles * ceil_div(a->N, 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
   const int n_tiles = ceil_div(a->N, BN);
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -567,9 +650,13 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (a_mn) rc = make_tmap_bf16_2d(&ma, a->A, a->M, a->K, a->lda, 64);
   else rc = make_tmap_bf16_2d(&ma, a->A, a->K, a->M, a->lda, TBM);
   if (rc) return rc;
+  CUtensorMap mb_half;  // B as loaded by one CTA of a pair: half of the tile's rows
   if (b_mn) rc = make_tmap_bf16_2d(&mb, a->B, a->N, a->K, a->ldb, 64);
   else rc = make_tmap_bf16_2d(&mb, a->B, a->K, a->N, a->ldb, BN);
   if (rc) return rc;
+  if (b_mn) mb_half = mb;
+  else if ((rc = make_tmap_bf16_2d(&mb_half, a->B, a->K, a->N, a->ldb, BN / 2))) return rc;
+  p.cta_group = (g_cta_group == 2 && m_tiles % 2 == 0) ? 2 : 1;
   // output through TMA when its pitch allows it (always true for the model's buffers)
   const int desz = a->d_dtype == DGPT_F32 ? 4 : 2;
   p.store_mode = kStoreDirect;
@@ -582,16 +669,14 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   }
   if (p.store_mode == kStoreDirect || a->D2 || (a->residual && a->relu_aux)) p.vec_ok = 0;  // everything through the compact element-wise path
 
-  const int total = m_tiles * n_tiles * p.split_k;
-  const int grid = min(total, sms);
   // epilogue specialisation: the combinations the model uses get their own instantiation, the rest run
   // the generic (run-time flag) kernel
   const int epi = (a->bias ? kEpiBias : 0) | (a->relu ? kEpiRelu : 0) | (a->relu_aux ? kEpiAux : 0) |
                   (a->dropout_p > 0.f ? kEpiDrop : 0) | (a->residual ? kEpiRes : 0);
 #ifdef DGPT_GEMM_TS
   {  // debug build: run synchronously and print the stamp deltas of the first three tiles of block 0
-    int rcx = (BN == 256) ? launch_cfg<256, 0, 0, kEpiBias | kEpiRelu>(ma, mb, md, p, grid, st)
-                          : launch_cfg<128, 0, 0, kEpiBias | kEpiRelu>(ma, mb, md, p, grid, st);
+    int rcx = (BN == 256) ? launch_cfg<256, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st)
+                          : launch_cfg<128, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st);
     cudaStreamSynchronize(st);
     long long h[3 * 64];
     cudaMemcpy(h, p.ts, sizeof(h), cudaMemcpyDeviceToHost);
@@ -605,7 +690,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   }
 #endif
 #define TC_EPI(BN_, A_, B_, E_) \
-  if (epi == (E_)) return launch_cfg<BN_, A_, B_, (E_)>(ma, mb, md, p, grid, st);
+  if (epi == (E_)) return launch_cfg<BN_, A_, B_, (E_)>(ma, mb, mb_half, md, p, sms, st);
 #define TC_DISPATCH(BN_)                                                          \
   if (BN == BN_) {                                                                \
     if (!a_mn && !b_mn) {                                                         \
@@ -614,15 +699,15 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
       TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu)                                      \
       TC_EPI(BN_, 0, 0, kEpiBias | kEpiRes)                                       \
       TC_EPI(BN_, 0, 0, kEpiBias | kEpiDrop | kEpiRes)                            \
-      return launch_cfg<BN_, 0, 0, -1>(ma, mb, md, p, grid, st);                  \
+      return launch_cfg<BN_, 0, 0, -1>(ma, mb, mb_half, md, p, sms, st);                  \
     }                                                                             \
     if (!a_mn && b_mn) {                                                          \
       TC_EPI(BN_, 0, 1, 0)                                                        \
       TC_EPI(BN_, 0, 1, kEpiAux)                                                  \
-      return launch_cfg<BN_, 0, 1, -1>(ma, mb, md, p, grid, st);                  \
+      return launch_cfg<BN_, 0, 1, -1>(ma, mb, mb_half, md, p, sms, st);                  \
     }                                                                             \
     TC_EPI(BN_, 1, 1, 0)                                                          \
-    return launch_cfg<BN_, 1, 1, -1>(ma, mb, md, p, grid, st);                    \
+    return launch_cfg<BN_, 1, 1, -1>(ma, mb, mb_half, md, p, sms, st);                    \
   }
   TC_DISPATCH(128)
   TC_DISPATCH(256)
