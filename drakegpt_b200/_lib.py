@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdrakegpt_b200.so")
+LIB_PATH = os.environ.get("DGPT_LIB") or os.path.join(_HERE, "csrc", "libdrakegpt_b200.so")  # DGPT_LIB: debug builds
 
 F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1

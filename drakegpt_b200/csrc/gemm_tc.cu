@@ -230,6 +230,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef DGPT_GEMM_TS
+  const long long t_block0 = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
@@ -267,7 +270,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ---------------------------
-    if (lane == 0) {
+    // the whole warp walks the loop (uniform control flow); one elected lane issues
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
@@ -279,6 +283,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
           const int k0 = kb * TBK;
+          if (!elect_one()) {
+            if (++s == kStages) { s = 0; ph ^= 1; }
+            continue;
+          }
           if (CG == 2) {
             // both CTAs load into their own shared memory; all bytes are credited to the LEADER's barrier,
             // which the leader arms for the pair's total
@@ -319,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer -----------------------------
-    if (lane == 0 && crank == 0) {  // with CG = 2 only the pair's leader issues MMAs
+    if (crank == 0) {  // with CG = 2 only the pair's leader issues MMAs; whole warp loops, one elected lane issues
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -335,23 +343,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
+          // K-major: 32 bytes per UMMA_K inside the 128B swizzle row, 8-row groups 1024 B apart.
+          // MN-major: 16 k-rows (2 KB) per UMMA_K, 64-element MN chunks 8 KB apart.
+          // (the start-address field counts 16-byte units: + 2 / + 128 per UMMA_K step)
+          const uint64_t da0 = A_MN ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db0 = B_MN ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            // K-major: 32 bytes per UMMA_K inside the 128B swizzle row, 8-row groups 1024 B apart.
-            // MN-major: 16 k-rows (2 KB) per UMMA_K, 64-element MN chunks 8 KB apart.
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (CG == 1) tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              const uint64_t da = da0 + (uint64_t)(k * (A_MN ? 128 : 2));
+              const uint64_t db = db0 + (uint64_t)(k * (B_MN ? 128 : 2));
+              if (CG == 1) tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CG == 1) tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
+            else tc_commit_2sm(&empty_bar[s]);      // ... in both CTAs of the pair
           }
-          if (CG == 1) tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
-          else tc_commit_2sm(&empty_bar[s]);      // ... in both CTAs of the pair
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        if (CG == 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        else tc_commit_2sm(&tmem_full[acc]);
+        if (elect_one()) {
+          if (CG == 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          else tc_commit_2sm(&tmem_full[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -489,6 +504,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+#ifdef DGPT_GEMM_TS
+  if (p.ts && threadIdx.x == 0) p.ts[1500 + blockIdx.x] = clock64() - t_block0;
+#endif
   if (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / retire while the pair's MMAs or arrives are in flight
   if (warp == 1) {
     tc_fence_after();
@@ -577,6 +595,21 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (CG == 2) {
+    // a persistent grid must not exceed the number of CTA pairs that can be resident at once (GPCs with an
+    // odd number of usable SMs leave single SMs that cannot host a pair)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(2 * 74);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();
+        max_clusters = 64;
+      }
+      if (getenv("DGPT_GEMM_VERBOSE")) fprintf(stderr, "gemm_tc: max active 2-CTA clusters = %d\n", max_clusters);
+    }
+    if (grid > 2 * max_clusters) cfg.gridDim = dim3((unsigned)(2 * max_clusters));
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc: launch: %s", cudaGetErrorString(e));
@@ -588,8 +621,15 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
 // Pair tiles (cta_group::2) are opt-in (dgpt_gemm_set_cta_group): on the model's shapes they measured no faster
 // than single-CTA tiles -- the 20-30 us GEMMs are bound by fixed per-launch / per-tile latencies and the
 // epilogue, not by operand delivery -- so the default stays 1.
-static int g_cta_group = 1;
+static int g_cta_group = -1;  // -1: not set yet (DGPT_GEMM_CTA_GROUP, default 1)
 void set_gemm_cta_group(int g) { g_cta_group = (g == 2) ? 2 : 1; }
+static int gemm_cta_group() {
+  if (g_cta_group < 0) {
+    const char* e = getenv("DGPT_GEMM_CTA_GROUP");
+    g_cta_group = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return g_cta_group;
+}
 
 // pair tiles whenever requested and the row-tile count is even, single-CTA tiles otherwise
 template <int BN, int A_MN, int B_MN, int EPI>
@@ -640,8 +680,8 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     p.debug = dbg;
 #ifdef DGPT_GEMM_TS
     static long long* ts = nullptr;
-    if (!ts) { cudaMalloc(&ts, 3 * 64 * sizeof(long long)); }
-    cudaMemset(ts, 0, 3 * 64 * sizeof(long long));
+    if (!ts) { cudaMalloc(&ts, 2048 * sizeof(long long)); }
+    cudaMemset(ts, 0, 2048 * sizeof(long long));
     p.ts = ts;
 #endif
   }
@@ -656,7 +696,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (rc) return rc;
   if (b_mn) mb_half = mb;
   else if ((rc = make_tmap_bf16_2d(&mb_half, a->B, a->K, a->N, a->ldb, BN / 2))) return rc;
-  p.cta_group = (g_cta_group == 2 && m_tiles % 2 == 0) ? 2 : 1;
+  p.cta_group = (gemm_cta_group() == 2 && m_tiles % 2 == 0) ? 2 : 1;
   // output through TMA when its pitch allows it (always true for the model's buffers)
   const int desz = a->d_dtype == DGPT_F32 ? 4 : 2;
   p.store_mode = kStoreDirect;
@@ -678,11 +718,18 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     int rcx = (BN == 256) ? launch_cfg<256, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st)
                           : launch_cfg<128, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st);
     cudaStreamSynchronize(st);
-    long long h[3 * 64];
+    long long h[2048];
     cudaMemcpy(h, p.ts, sizeof(h), cudaMemcpyDeviceToHost);
+    {
+      printf("block durations (cycles):");
+      for (int i = 0; i < 148; ++i) printf(" %lld", h[1500 + i]);
+      printf("\n");
+    }
     for (int t = 0; t < 3; ++t) {
       printf("tile %d:", t);
       for (int i = 1; i < 48 && h[t * 64 + i]; ++i) printf(" %lld", h[t * 64 + i] - h[t * 64 + i - 1]);
+      printf("\nblock durations (cycles):");
+      for (int i = 0; i < 148; ++i) printf(" %lld", h[1500 + i]);
       printf("\n");
     }
     fflush(stdout);

@@ -1,4 +1,11 @@
-"""Run the tcgen05 GEMM at the scaled-model shapes a few times (ncu target + quick timing)."""
+"""Time the tcgen05 GEMM at the scaled-model shapes.
+
+Each shape is launched R times back to back inside ONE CUDA graph, every launch on its own
+operand/output buffers (R sets, together larger than the 126 MB L2, so operands come from HBM as
+they do inside the training step), and the graph replay is timed with CUDA events: the number is
+device time per launch, free of host launch latency.  `python tools/gemm_probe.py [names...]`;
+with `--single` each launch is timed alone after an L2 flush (ncu target).
+"""
 import sys, os, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,15 +14,31 @@ from drakegpt_b200._lib import MAJOR_K, MAJOR_MN
 
 dev = "cuda"
 shapes = {  # name: (M, N, K, a_major, b_major, out dtype, epilogue)
+    "qkv_fwd": (16384, 1152, 384, MAJOR_K, MAJOR_K, torch.bfloat16, "none"),
+    "proj_fwd": (16384, 384, 384, MAJOR_K, MAJOR_K, torch.float32, "bias_drop_res"),
     "ffn1_fwd": (16384, 1536, 384, MAJOR_K, MAJOR_K, torch.bfloat16, "bias_relu"),
     "ffn2_fwd": (16384, 384, 1536, MAJOR_K, MAJOR_K, torch.float32, "bias_drop_res"),
-    "qkv_fwd": (16384, 1152, 384, MAJOR_K, MAJOR_K, torch.bfloat16, "none"),
     "ffn2_dgrad": (16384, 1536, 384, MAJOR_K, MAJOR_MN, torch.bfloat16, "relu_aux"),
+    "ffn1_dgrad": (16384, 384, 1536, MAJOR_K, MAJOR_MN, torch.bfloat16, "none"),
+    "qkv_dgrad": (16384, 384, 1152, MAJOR_K, MAJOR_MN, torch.bfloat16, "none"),
+    "proj_dgrad": (16384, 384, 384, MAJOR_K, MAJOR_MN, torch.bfloat16, "none"),
     "ffn1_wgrad": (1536, 384, 16384, MAJOR_MN, MAJOR_MN, torch.float32, "splitk"),
+    "ffn2_wgrad": (384, 1536, 16384, MAJOR_MN, MAJOR_MN, torch.float32, "splitk"),
+    "qkv_wgrad": (1152, 384, 16384, MAJOR_MN, MAJOR_MN, torch.float32, "splitk"),
+    "proj_wgrad": (384, 384, 16384, MAJOR_MN, MAJOR_MN, torch.float32, "splitk"),
 }
-which = sys.argv[1:] or list(shapes)
-flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-for name in which:
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+single = "--single" in sys.argv
+which = args or list(shapes)
+R = 6
+
+
+def splits(rows, cols, k, sm=148):
+    tiles = ((rows + 127) // 128) * ((cols + 127) // 128)
+    return max(1, min(sm // max(tiles, 1), k // 512))
+
+
+def make(name):
     M, N, K, am, bm, odt, epi = shapes[name]
     A = torch.randn((M, K) if am == MAJOR_K else (K, M), device=dev).bfloat16()
     B = torch.randn((N, K) if bm == MAJOR_K else (K, N), device=dev).bfloat16()
@@ -28,15 +51,41 @@ for name in which:
     elif epi == "relu_aux":
         kw = dict(relu_aux=torch.randn(M, N, device=dev).bfloat16())
     elif epi == "splitk":
-        kw = dict(accumulate=True, split_k=4)
-    ts = []
-    for i in range(8):
-        flush.zero_()
+        kw = dict(accumulate=True, split_k=splits(M, N, K))
+    return lambda: ops.raw_gemm(A, B, out, a_major=am, b_major=bm, **kw)
+
+
+flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+for name in which:
+    M, N, K = shapes[name][:3]
+    if single:
+        fn = make(name)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        t = statistics.mean(ts)
+    else:
+        fns = [make(name) for _ in range(R)]
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for rep in range(4):
+                for f in fns:
+                    f()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.raw_gemm(A, B, out, a_major=am, b_major=bm, **kw)
+        for _ in range(5):
+            g.replay()
         e1.record(); e1.synchronize()
-        if i >= 3:
-            ts.append(e0.elapsed_time(e1) * 1e3)
-    t = statistics.mean(ts)
+        t = e0.elapsed_time(e1) * 1e3 / (5 * 4 * R)
     print(f"{name}: {t:.1f} us  {2.0*M*N*K/t/1e6:.0f} TFLOP/s", flush=True)
