@@ -105,7 +105,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(qk_full, 16384 * (1 + nkv));
       tma_load_2d(sQ, &map_q, qk_full, h * HD, row0 + qt * QT);
       for (int j = 0; j < nkv; ++j) tma_load_2d(sK + j * 16384, &map_k, qk_full, h * HD, row0 + j * QT);
@@ -113,31 +113,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int kb = 0; kb < 2 * nkv; ++kb) tma_load_2d(sV + kb * 8192, &map_v, v_full, h * HD, row0 + kb * 64);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      mbar_wait(qk_full, 0);
-      tc_fence_after();
-      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+    // the whole warp walks the (uniform) control flow, one elected lane issues: descriptors stay in uniform
+    // registers (an `if (lane == 0)` region makes the compiler wrap every MMA in an R2UR waterfall loop)
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+    mbar_wait(qk_full, 0);
+    tc_fence_after();
+    const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    if (elect_one()) {
       for (int j = 0; j < nkv; ++j) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + j * 128, make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                      make_smem_desc_sw128(ak + j * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+          tc_mma_bf16(tmem + j * 128, dq0 + (uint64_t)(k * 2), dk0 + (uint64_t)(j * 1024 + k * 2), idesc_s, k > 0);
       }
       tc_commit(s_full);
-      mbar_wait(v_full, 0);
-      mbar_wait(p_full, 0);
-      tc_fence_after();
-      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+    }
+    __syncwarp();
+    mbar_wait(v_full, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+    if (elect_one()) {
       for (int kb = 0; kb < 2 * nkv; ++kb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem, make_smem_desc_sw128(ap + kb * 16384 + k * 32, 16, 1024),
-                      make_smem_desc_sw128(av + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) > 0);
+          tc_mma_bf16(tmem, dp0 + (uint64_t)(kb * 1024 + k * 2), dv0 + (uint64_t)(kb * 512 + k * 128), idesc_o, (kb | k) > 0);
       }
       tc_commit(o_full);
     }
+    __syncwarp();
   } else {
     // ---------------------------- softmax + epilogue: one thread per query row ----------
     const int quad = warp & 3;
@@ -317,7 +323,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(ld_full, 16384 * 5 * ntile);
       for (int t = 0; t < ntile; ++t) {
         tma_load_2d(sG + t * 16384, &map_do, ld_full, h * HD, row0 + t * QT);
@@ -328,52 +334,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP
-      constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dQ
-      constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dV, dK
-      mbar_wait(ld_full, 0);
-      tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG);
-      const uint32_t aPd = smem_u32(sPd), aDs = smem_u32(sDs);
-      for (int pr = 0; pr < npair; ++pr) {
-        const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
-        const uint32_t ph = pr & 1;
-        // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal
-        // test and the dropout quads (which run along the key axis) are per-thread like in forward
+    // whole warp in uniform control flow, one elected lane issues (see forward)
+    constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP
+    constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dQ
+    constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dV, dK
+    mbar_wait(ld_full, 0);
+    tc_fence_after();
+    // descriptor bases; the start-address field counts 16-byte units (a 16 KB tile = 1024, 2 KB = 128, 32 B = 2)
+    const uint64_t kQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), kK = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t kV = make_smem_desc_sw128(smem_u32(sV), 16, 1024), kG = make_smem_desc_sw128(smem_u32(sG), 16, 1024);
+    const uint64_t kDs = make_smem_desc_sw128(smem_u32(sDs), 16, 1024);
+    const uint64_t mQ = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024), mK = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);
+    const uint64_t mG = make_smem_desc_sw128(smem_u32(sG), 8192, 1024);
+    const uint64_t mPd = make_smem_desc_sw128(smem_u32(sPd), 16384, 1024), mDs = make_smem_desc_sw128(smem_u32(sDs), 16384, 1024);
+    for (int pr = 0; pr < npair; ++pr) {
+      const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+      const uint32_t ph = pr & 1;
+      // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal
+      // test and the dropout quads (which run along the key axis) are per-thread like in forward
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + TM_ST, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aK + j * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+          tc_mma_bf16(tmem + TM_ST, kQ + (uint64_t)(i * 1024 + k * 2), kK + (uint64_t)(j * 1024 + k * 2), id_kk, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + TM_DP, make_smem_desc_sw128(aG + i * 16384 + k * 32, 16, 1024),
-                      make_smem_desc_sw128(aV + j * 16384 + k * 32, 16, 1024), id_kk, k > 0);
+          tc_mma_bf16(tmem + TM_DP, kG + (uint64_t)(i * 1024 + k * 2), kV + (uint64_t)(j * 1024 + k * 2), id_kk, k > 0);
         tc_commit(st_full);
-        mbar_wait(ps_full, ph);
-        if (pr > 0) mbar_wait(drained, (pr - 1) & 1);
-        tc_fence_after();
-        const uint32_t acc_vk = (pr == 1) ? 1u : 0u;  // second pair of key tile 0 accumulates
-        const uint32_t acc_q = (pr == 2) ? 1u : 0u;   // second pair of query tile 1 accumulates
+      }
+      __syncwarp();
+      mbar_wait(ps_full, ph);
+      if (pr > 0) mbar_wait(drained, (pr - 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_vk = (pr == 1) ? 1u : 0u;  // second pair of key tile 0 accumulates
+      const uint32_t acc_q = (pr == 2) ? 1u : 0u;   // second pair of query tile 1 accumulates
+      if (elect_one()) {
         // dV_j += Pd^T dO_i, dK_j += dS^T Q_i: A = the [q x kv] tile read MN-major (M = kv: 64-wide
         // chunks 16 KB apart, K = q rows); B = dO_i / Q_i read MN-major (N = d, K = q rows)
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          tc_mma_bf16(tmem + TM_DV, make_smem_desc_sw128(aPd + k * 2048, 16384, 1024),
-                      make_smem_desc_sw128(aG + i * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_vk | (k > 0));
+          tc_mma_bf16(tmem + TM_DV, mPd + (uint64_t)(k * 128), mG + (uint64_t)(i * 1024 + k * 128), id_mnmn, acc_vk | (k > 0));
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          tc_mma_bf16(tmem + TM_DK, make_smem_desc_sw128(aDs + k * 2048, 16384, 1024),
-                      make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024), id_mnmn, acc_vk | (k > 0));
+          tc_mma_bf16(tmem + TM_DK, mDs + (uint64_t)(k * 128), mQ + (uint64_t)(i * 1024 + k * 128), id_mnmn, acc_vk | (k > 0));
         // dQ_i += dS K_j: A = dS K-major over kv (two 64-wide k-blocks), B = K_j MN-major (N = d, K = kv rows)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t a_k = (k >> 2) * 16384 + (k & 3) * 32;
-          tc_mma_bf16(tmem + TM_DQ, make_smem_desc_sw128(aDs + a_k, 16, 1024),
-                      make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_kmn, acc_q | (k > 0));
-        }
+        for (int k = 0; k < 8; ++k)
+          tc_mma_bf16(tmem + TM_DQ, kDs + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), mK + (uint64_t)(j * 1024 + k * 128), id_kmn,
+                      acc_q | (k > 0));
         if (pr == npair - 1) tc_commit(acc_done);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------ 256 compute threads --------------------------------

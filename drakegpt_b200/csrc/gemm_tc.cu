@@ -29,142 +29,113 @@ static constexpr int TBM = 128;       // tile M (UMMA M)
 static constexpr int TBK = 64;        // k-block: 64 bf16 = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int kThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps
-static constexpr int kStageBudget = 160 * 1024;
-static constexpr int kStagingBytes = 8 * 2 * 4096;  // 8 epilogue warps x 2 buffers x (32 rows x 128 B)
+static constexpr int kSmemMax = 232448;    // 227 KB per CTA on sm_100
 
 enum StoreMode { kStoreDirect = 0, kStoreTma = 1, kStoreTmaAdd = 2 };
 
 struct TcParams {
   int M, N, K;
   int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
-  int vec_ok;      // epilogue operands (bias / residual / relu_aux) allow 16-byte loads
+  int vec_ok;      // epilogue operands (bias / residual) allow the vector fast path
   int store_mode;  // StoreMode for D
   int cta_group;   // 1, or 2 = CTA pairs (cluster of 2) sharing each MMA
-#ifdef DGPT_GEMM_TS
-  long long* ts;   // cycle stamps of (block 0, first epilogue warp, lane 0) for the first tiles (debug builds)
-#endif
   int debug;       // DGPT_GEMM_DEBUG: 1 = epilogue skipped, 2 = no TMA loads / MMAs (timing experiments only)
+  uint32_t* mask_out;        // ReLU bit mask written by the forward GEMM  [(n / 32) * M + m]
+  const uint32_t* mask_in;   // ... and applied by the dgrad GEMM
   Epilogue ep;
 };
 
+// epilogue feature bits (compile-time mask of the fused epilogue, or -1 = generic element-wise path)
+enum { kEpiBias = 1, kEpiRelu = 2, kEpiAux = 4, kEpiDrop = 8, kEpiRes = 16, kEpiMaskIn = 32, kEpiMaskOut = 64 };
+
 // CG = CTAs sharing one MMA (tcgen05 cta_group).  With CG = 2 a pair of CTAs computes a 256 x BN tile: each CTA
-// stages its own 128 rows of A but only HALF of B (the MMA reads the other half from the peer's shared
-// memory), so every SM ingests and re-reads a third (BN = 256) or a quarter (BN = 128) fewer operand
-// bytes per MMA cycle -- operand delivery (L2 -> SM ~43 B/cycle/SM measured) and shared-memory bandwidth
-// are what bound the single-CTA mainloop.
-template <int BN, int CG = 1>
+// stages its own 128 rows of A but only HALF of B (the MMA reads the other half from the peer's shared memory).
+// RESBUFS != 0: the fp32 residual operand arrives by TMA into the epilogue staging buffers, see the epilogue below.
+// 4 buffers per warp = the next tile's residual is fetched while this tile's stores drain (short-K GEMMs, whose
+// epilogue is the critical path; ring of 3 stages); 2 buffers = fetched once this tile's stores have been read
+// (long-K GEMMs: the epilogue warps have slack, the mainloop wants the 5-stage ring).
+template <int BN, int CG, int RESBUFS>
 struct TcCfg {
   static constexpr int kBBytes = (BN / CG) * TBK * 2;
   static constexpr int kStageBytes = TBM * TBK * 2 + kBBytes;
-  static constexpr int kStages = kStageBudget / kStageBytes > 8 ? 8 : kStageBudget / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
+  static constexpr int kStagingBufs = RESBUFS ? RESBUFS : 2;       // 4 KB staging buffers per epilogue warp
+  static constexpr int kStagingBytes = 8 * kStagingBufs * 4096;
   static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + 256 /*barriers*/;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kRing = kSmemMax - kStagingBytes - kBiasBytes - kBarBytes;
+  static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
+  static_assert(kStages >= 3, "shared-memory ring too shallow");
 };
 
 // --------------------------------------------------------------------------
-// epilogue math on 32 consecutive columns [n, n+32) of accumulator row m (all in registers).
-// Fast path only: n + 32 <= N, 16-byte aligned operands.  Keep this small -- the kernel's
-// instruction footprint must stay inside the instruction cache (an earlier version that
-// unrolled the ragged path 32x was 180 KB of SASS and stalled on instruction fetch).
+// Fast epilogue math on 32 consecutive accumulator columns [n, n+32) of row m, in registers.
+// Order (= epilogue_value): + bias, ReLU (+ bit mask out), bit mask in, dropout, + residual.
+//   bias_s  : the tile's bias slice in shared memory (broadcast reads)
+//   res_row : this row of the 32 x 32 fp32 residual block the TMA put into the staging buffer (SW128)
+// Keep this small: the kernel's instruction footprint must stay inside the instruction cache.
 // --------------------------------------------------------------------------
-// `pre` holds the chunk's residual (8 x float4) or ReLU-mask operand (4 x uint4 of bf16 / 8 x float4 of
-// fp32), fetched one chunk ahead; `bias_s` is the tile's bias slice in shared memory.  (With ~226 KB
-// of shared memory in use the L1 data cache is nearly gone: an un-prefetched global load here costs a
-// full L2 round trip per chunk on the only warp of the scheduler, which is what bounded the epilogue.)
-// EPI: compile-time feature mask of the fused epilogue (kEpiBias | kEpiRelu | ...), or -1 to test the
-// run-time flags.  The specialisations matter: with run-time flags the compiler if-converts the whole
-// body (~600 predicated instructions per 32-column step, measured 700 cycles) instead of ~100.
-enum { kEpiBias = 1, kEpiRelu = 2, kEpiAux = 4, kEpiDrop = 8, kEpiRes = 16 };
-template <int EPI> __device__ __forceinline__ bool epi_has(int bit, bool runtime) { return EPI < 0 ? runtime : (EPI & bit) != 0; }
-
 template <int EPI>
-__device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int m, int n, uint4 (&pre)[8]) {
-  if (e.first_split && epi_has<EPI>(kEpiRes, e.residual != nullptr)) {
-    const uint4* rp = reinterpret_cast<const uint4*>(e.residual + (int64_t)m * e.ldr + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pre[j] = __ldg(rp + j);
-  } else if (epi_has<EPI>(kEpiAux, e.relu_aux != nullptr)) {
-    if (e.aux_dtype == DGPT_BF16) {
-      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pre[j] = __ldg(ap + j);
-    } else {
-      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.relu_aux) + (int64_t)m * e.ld_aux + n);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pre[j] = __ldg(ap + j);
-    }
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epilogue_math32(const Epilogue& e, int m, int n, float (&v)[32], const float* bias_s,
-                                                const uint4 (&pre)[8]) {
-  if (e.first_split && epi_has<EPI>(kEpiBias, e.bias != nullptr)) {
+__device__ __forceinline__ void epi_math32(const Epilogue& e, int m, int n, uint32_t (&r)[32], const float* bias_s,
+                                           const uint8_t* res_row, int row7, uint32_t mask_in, uint32_t& mask_out) {
+  if (EPI & kEpiBias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(bias_s + j);  // shared-memory broadcast
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      r[j] = __float_as_uint(__uint_as_float(r[j]) + b.x);
+      r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b.y);
+      r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b.z);
+      r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b.w);
     }
   }
-  if (epi_has<EPI>(kEpiRelu, e.relu != 0)) {
+  if (EPI & kEpiMaskOut) {
+    uint32_t mk = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 32; ++j) mk |= (__uint_as_float(r[j]) > 0.f) ? (1u << j) : 0u;
+    mask_out = mk;
   }
-  if (epi_has<EPI>(kEpiAux, e.relu_aux != nullptr)) {
-    if (e.aux_dtype == DGPT_BF16) {
+  if (EPI & kEpiRelu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t w[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-          const uint32_t lo = w[t] & 0xFFFFu, hi = w[t] >> 16;
-          if (!(lo != 0 && lo < 0x8000u)) v[j * 8 + t * 2] = 0.f;
-          if (!(hi != 0 && hi < 0x8000u)) v[j * 8 + t * 2 + 1] = 0.f;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!(__uint_as_float(pre[j].x) > 0.f)) v[4 * j] = 0.f;
-        if (!(__uint_as_float(pre[j].y) > 0.f)) v[4 * j + 1] = 0.f;
-        if (!(__uint_as_float(pre[j].z) > 0.f)) v[4 * j + 2] = 0.f;
-        if (!(__uint_as_float(pre[j].w) > 0.f)) v[4 * j + 3] = 0.f;
-      }
-    }
+    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
   }
-  if (epi_has<EPI>(kEpiDrop, e.thr != 0)) {
+  if (EPI & kEpiMaskIn) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = ((mask_in >> j) & 1u) ? r[j] : 0u;
+  }
+  if (EPI & kEpiDrop) {
     const uint64_t q0 = ((uint64_t)m * (uint64_t)e.N + (uint64_t)n) >> 2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const u32x4 b = dropout_bits4(e.seed, e.site, q0 + j);
-      v[4 * j] = b.x >= e.thr ? v[4 * j] * e.inv_keep : 0.f;
-      v[4 * j + 1] = b.y >= e.thr ? v[4 * j + 1] * e.inv_keep : 0.f;
-      v[4 * j + 2] = b.z >= e.thr ? v[4 * j + 2] * e.inv_keep : 0.f;
-      v[4 * j + 3] = b.w >= e.thr ? v[4 * j + 3] * e.inv_keep : 0.f;
+      r[4 * j] = b.x >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j]) * e.inv_keep) : 0u;
+      r[4 * j + 1] = b.y >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 1]) * e.inv_keep) : 0u;
+      r[4 * j + 2] = b.z >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 2]) * e.inv_keep) : 0u;
+      r[4 * j + 3] = b.w >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 3]) * e.inv_keep) : 0u;
     }
   }
-  if (e.first_split && epi_has<EPI>(kEpiRes, e.residual != nullptr)) {
+  if (EPI & kEpiRes) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[4 * j] += __uint_as_float(pre[j].x); v[4 * j + 1] += __uint_as_float(pre[j].y);
-      v[4 * j + 2] += __uint_as_float(pre[j].z); v[4 * j + 3] += __uint_as_float(pre[j].w);
+      const float4 x = *reinterpret_cast<const float4*>(res_row + ((j ^ row7) << 4));
+      r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + x.x);
+      r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + x.y);
+      r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + x.z);
+      r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + x.w);
     }
   }
 }
 
-// Ragged edge (n + 32 > N), unaligned operands, outputs the TMA cannot address, and the optional
-// second output: one compact element-wise loop over a local copy of the 32 values.
-// (Epilogue BY VALUE: a reference would pin the caller's copy in local memory, turning every flag test of
-// the fast path into a local-memory load.)
-__device__ __noinline__ void epilogue_slow32(const Epilogue e, float* v, int m, int n, int store_main) {
+// Ragged edge (n + 32 > N), unaligned operands, outputs the TMA cannot address, the optional second
+// output and every combination without its own instantiation: one compact element-wise loop.
+// (Epilogue BY VALUE: a reference would pin the caller's copy in local memory.)
+__device__ __noinline__ void epilogue_slow32(const Epilogue e, uint32_t* r, int m, int n, int store_main) {
   if (m >= e.M) return;
 #pragma unroll 1
   for (int j = 0; j < 32; ++j) {
     if (n + j >= e.N) break;
-    const float x = epilogue_value(e, m, n + j, v[j]);
-    v[j] = x;
+    const float x = epilogue_value(e, m, n + j, __uint_as_float(r[j]));
+    r[j] = __float_as_uint(x);
     if (store_main) {
       const int64_t i = (int64_t)m * e.ldd + n + j;
       if (e.d_dtype == DGPT_F32) {
@@ -183,19 +154,19 @@ __device__ __noinline__ void epilogue_slow32(const Epilogue e, float* v, int m, 
   }
 }
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b));
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
 // one row (128 bytes) of a 32-row SWIZZLE_128B staging tile
-__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int row, const float (&v)[32]) {
+__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int row, const uint32_t (&v)[32]) {
   uint8_t* rp = tile + row * 128;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(rp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<uint4*>(rp + ((j ^ (row & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
-__device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int half, const float (&v)[32]) {
+__device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int half, const uint32_t (&v)[32]) {
   uint8_t* rp = tile + row * 128;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -208,12 +179,16 @@ __device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int 
 
 // --------------------------------------------------------------------------
 // the kernel
+//   EPI  : compile-time epilogue feature mask (fast path), or -1 = generic element-wise epilogue
+//   OBF  : output element type of the fast path (1 = bf16, 0 = fp32); ignored when EPI < 0
 // --------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN, int EPI, int CG>
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_d, TcParams p) {
-  using Cfg = TcCfg<BN, CG>;
+               const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r, TcParams p) {
+  constexpr bool kRes = EPI >= 0 && (EPI & kEpiRes) != 0;
+  static_assert(kRes == (RESBUFS != 0), "RESBUFS goes with the residual epilogues");
+  using Cfg = TcCfg<BN, CG, RESBUFS>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = TBM * TBK * 2;
   constexpr int kBBytes = Cfg::kBBytes;
@@ -222,22 +197,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + (size_t)kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 8 KB
-  float* bias_s = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + Cfg::kBiasBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);  // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kBiasBytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full = empty_bar + 8;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // [8 epilogue warps][2 tiles in flight]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#ifdef DGPT_GEMM_TS
-  const long long t_block0 = clock64();
-#endif
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     if (p.store_mode != kStoreDirect) prefetch_tensormap(&map_d);
+    if (kRes) prefetch_tensormap(&map_r);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -246,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8 * CG);  // one arrive per epilogue warp of every CTA sharing the accumulator
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (CG == 2) {  // both CTAs of the pair have initialised their barriers before the paired TMEM allocation
@@ -271,22 +246,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ------------------------------ TMA producer ---------------------------
     // the whole warp walks the loop (uniform control flow); one elected lane issues
-    {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
-        const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-        const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          const int k0 = kb * TBK;
-          if (!elect_one()) {
-            if (++s == kStages) { s = 0; ph ^= 1; }
-            continue;
-          }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_first; t < total_tiles; t += t_step) {
+      const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        const int k0 = kb * TBK;
+        if (elect_one()) {
           if (CG == 2) {
             // both CTAs load into their own shared memory; all bytes are credited to the LEADER's barrier,
             // which the leader arms for the pair's total
@@ -305,24 +276,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else {
               tma_load_2d_2sm(sb, &map_b, lbar, k0, nh);
             }
-            if (++s == kStages) { s = 0; ph ^= 1; }
-            continue;
-          }
-          mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
-          if (A_MN) {
-#pragma unroll
-            for (int c = 0; c < TBM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
           } else {
-            tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
-          }
-          if (B_MN) {
+            mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+            if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &map_b, &full_bar[s], n0 + c * 64, k0);
-          } else {
-            tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+              for (int c = 0; c < TBM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
+            } else {
+              tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &map_b, &full_bar[s], n0 + c * 64, k0);
+            } else {
+              tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+            }
           }
-          if (++s == kStages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -372,130 +343,161 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ------------------------------ epilogue -------------------------------
-    // Eight warps: TMEM lane quadrant = warp % 4 (hardware rule), and the two warps of a quadrant
-    // split the tile's columns.  Two warps per scheduler hide each other's fixed latencies
-    // (measured per 32-column step of one warp: tcgen05.ld+wait ~590 cycles, bias/ReLU ~400,
-    // pack+STS ~190, fence+TMA store ~260); the TMEM load of step i+1 is issued before step i's math.
+    // Eight warps: TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the tile's
+    // columns.  Work unit = one 4 KB staging block: 32 rows x 128 bytes of OUTPUT (64 bf16 / 32 fp32 columns):
+    //   tcgen05.ld (TMEM reads are cheap: ~40 cycles for 4 x 32 columns, measured) -> math in registers ->
+    //   one swizzled 128-byte row per thread into the block -> fence.proxy.async -> one TMA store / reduce.
+    // A warp's blocks rotate through its staging buffers; cp.async.bulk.wait_group.read keeps a buffer from
+    // being rewritten while an earlier store still reads it.
+    // Residual (kRes): row-strided loads of the fp32 residual cost 32 L1 wavefronts per instruction (measured
+    // +18 us on a 9 us GEMM), so the TMA fetches the residual block INTO the staging buffer the output will
+    // leave from -- for the NEXT tile, while this one is computed -- and the add happens in place.
     const int ew = warp - 2;
     const int quad = warp & 3;   // TMEM lanes [32*quad, 32*quad+32)
     const int half = ew >> 2;    // columns [half*BN/2, (half+1)*BN/2)
     constexpr int kCols = BN / 2;
-    uint8_t* my_stage = staging + ew * 8192;
-    int sbuf = 0;
+    constexpr bool kFast = EPI >= 0;
+    constexpr int CPB = (kFast && OBF) ? 64 : 32;  // accumulator columns per staging block (fast path; residual bookkeeping)
+    constexpr int NBLK = kCols / CPB;
+    constexpr int kBufs = Cfg::kStagingBufs;
+    uint8_t* my_stage = staging + ew * (kBufs * 4096);
+    uint64_t* my_res_bar = res_bar + ew * 2;
+    int nbuf = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
+    int it = 0;
     Epilogue ep = p.ep;
     epilogue_resolve_seed(ep);
-    const bool bf16_out = ep.d_dtype == DGPT_BF16;
     const int mode = p.store_mode;
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    const bool out_bf16 = kFast ? (OBF != 0) : (ep.d_dtype == DGPT_BF16);
+    const int cpb = out_bf16 ? 64 : 32;  // compile-time on the fast path, run-time in the generic kernel
+    const int nblk = kCols / cpb;
+    const int row7 = lane & 7;
+
+    constexpr bool kResAhead = RESBUFS == 4;  // a second buffer pair: fetch a whole tile ahead
+    auto res_prefetch = [&](int t, int par) {  // lane 0: residual blocks of tile t -> buffers [NBLK par, NBLK par + NBLK)
+      const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int nb = n0 + half * kCols;
+      int cnt = 0;
+      for (int b = 0; b < NBLK; ++b) cnt += (nb + b * CPB < p.N) ? 1 : 0;
+      if (cnt == 0 || m0 + quad * 32 >= p.M) { mbar_arrive(&my_res_bar[par]); return; }
+      mbar_expect_tx(&my_res_bar[par], cnt * 4096);
+      for (int b = 0; b < NBLK; ++b)
+        if (nb + b * CPB < p.N) tma_load_2d(my_stage + (par * NBLK + b) * 4096, &map_r, &my_res_bar[par], nb + b * CPB, m0 + quad * 32);
+    };
+    if (kRes && lane == 0 && t_first < total_tiles && !(p.debug & 1)) res_prefetch(t_first, 0);
+
+    for (int t = t_first; t < total_tiles; t += t_step, ++it) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
       ep.first_split = (ks == 0);
       const int mrow0 = (p.debug & 1) ? p.M : m0 + quad * 32;  // debug bit 0: skip all epilogue work
       const int m = mrow0 + lane;
-      const bool row_ok = m < p.M;
+      const int nbeg = n0 + half * kCols;
+      const bool active = mrow0 < p.M && nbeg < p.N;
       // stage this tile's bias slice (each warp an eighth) while the accumulator is still being produced
       float* bias_t = bias_s + acc * BN;
-      if (p.vec_ok && ep.first_split && epi_has<EPI>(kEpiBias, ep.bias != nullptr)) {
+      if (kFast && (EPI & kEpiBias)) {
         const int col = ew * (BN / 8) + lane * 4;
         if (lane * 4 < BN / 8 && n0 + col < p.N)
           *reinterpret_cast<float4*>(bias_t + col) = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + col));
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
-      const int nbeg = n0 + half * kCols;
-      const bool active = mrow0 < p.M && nbeg < p.N;
-      uint4 pre[8];
-      if (p.vec_ok && row_ok && nbeg + 32 <= p.N) epilogue_prefetch<EPI>(ep, m, nbeg, pre);
-#ifdef DGPT_GEMM_TS
-      const bool stamp = p.ts && blockIdx.x == 0 && warp == 2 && lane == 0 && t < 3 * t_step;
-      long long* tsp = p.ts + (t / t_step) * 64;
-      int tsi = 0;
-#define TS_MARK() do { if (stamp) tsp[tsi++] = clock64(); } while (0)
-#else
-#define TS_MARK() do { } while (0)
-#endif
-      TS_MARK();
+      uint32_t mk_in[kCols / 32];
+      if (kFast && (EPI & kEpiMaskIn)) {
+#pragma unroll
+        for (int w = 0; w < kCols / 32; ++w)
+          mk_in[w] = (active && m < p.M && nbeg + 32 * w < p.N) ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + m) : 0u;
+      }
+      const int par = kResAhead ? (it & 1) : 0;
+      if (kRes && !(p.debug & 1)) mbar_wait(&my_res_bar[par], (uint32_t)(kResAhead ? (it >> 1) : it) & 1u);
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      TS_MARK();
       const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kCols);
-      // 32 accumulator columns per step; a staging tile (32 rows x 128 B) holds 32 fp32 or 64 bf16
-      // columns, so bf16 output issues one TMA store every second step
-      uint8_t* tile = my_stage + sbuf * 4096;
-      uint32_t r[32];
-#ifdef DGPT_GEMM_TS
-      {  // micro-benchmark: 1 load vs 4 back-to-back loads (latency- or throughput-bound?)
-        uint32_t q0[32], q1[32], q2[32], q3[32];
-        TS_MARK();
-        tmem_ld32(row_addr, q0);
-        tmem_ld_wait();
-        TS_MARK();
-        tmem_ld32(row_addr, q0); tmem_ld32(row_addr + 32, q1); tmem_ld32(row_addr + 64, q2); tmem_ld32(row_addr + 96, q3);
-        tmem_ld_wait();
-        TS_MARK();
-        uint32_t x = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x ^= q0[j] ^ q1[j] ^ q2[j] ^ q3[j];
-        if (x == 0x12345678u) tile[0] = 1;
-        TS_MARK();
-      }
-#endif
-      if (active) tmem_ld32(row_addr, r);
 #pragma unroll 1
-      for (int c = 0; c < kCols && active; c += 32) {
-        const int n = nbeg + c;
-        if (n >= p.N) break;
-        const bool opens_tile = !bf16_out || (c & 32) == 0;
-        if (mode != kStoreDirect && opens_tile) {
-          tile = my_stage + sbuf * 4096;
-          if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has drained this buffer
+      for (int b = 0; b < nblk; ++b) {
+        const int n = nbeg + b * cpb;
+        const bool in_range = active && n < p.N;
+        uint8_t* tile = kRes ? my_stage + (par * NBLK + b) * 4096 : my_stage + nbuf * 4096;
+        if (!in_range) {
+          if (kRes && lane == 0 && mode != kStoreDirect) bulk_commit();  // keep one bulk group per block (see wait below)
+          continue;
+        }
+        uint32_t r0[32], r1[32];
+        tmem_ld32(row_addr + b * cpb, r0);
+        if (cpb == 64) tmem_ld32(row_addr + b * cpb + 32, r1);
+        if (!kRes && mode != kStoreDirect) {
+          if (lane == 0) bulk_wait_read<kBufs - 1>();  // the store that last used this buffer has drained it
           __syncwarp();
         }
-        TS_MARK();
         tmem_ld_wait();
-        TS_MARK();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool has_next = c + 32 < kCols && n + 32 < p.N;
-        if (has_next) tmem_ld32(row_addr + c + 32, r);  // in flight during this step's math
-        if (p.vec_ok && n + 32 <= p.N && row_ok) {
-          epilogue_math32<EPI>(ep, m, n, v, bias_t + half * kCols + c, pre);
+        const bool fast = kFast && p.vec_ok && mode != kStoreDirect && n + cpb <= p.N;
+        if (fast) {
+          uint32_t mo = 0;
+          epi_math32<kFast ? EPI : 0>(ep, m, n, r0, bias_t + half * kCols + b * cpb, tile + lane * 128, row7,
+                                      (kFast && (EPI & kEpiMaskIn)) ? mk_in[(b * cpb) >> 5] : 0u, mo);
+          if (kFast && (EPI & kEpiMaskOut)) {
+            if (m < p.M) p.mask_out[(size_t)(n >> 5) * p.M + m] = mo;
+          }
+          if (cpb == 64) {
+            epi_math32<kFast ? EPI : 0>(ep, m, n + 32, r1, bias_t + half * kCols + b * cpb + 32, tile + lane * 128, row7,
+                                        (kFast && (EPI & kEpiMaskIn)) ? mk_in[((b * cpb) >> 5) + 1] : 0u, mo);
+            if (kFast && (EPI & kEpiMaskOut)) {
+              if (m < p.M) p.mask_out[(size_t)((n >> 5) + 1) * p.M + m] = mo;
+            }
+          }
         } else {
-          float tmp[32];
+          // (through a local copy: passing r0 / r1 themselves would pin them in local memory for the fast path too)
+          uint32_t tmp[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+          for (int j = 0; j < 32; ++j) tmp[j] = r0[j];
           epilogue_slow32(ep, tmp, m, n, mode == kStoreDirect);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tmp[j];
-        }
-        // operands of the next step: in flight during the staging / store below and the next TMEM wait
-        if (has_next && p.vec_ok && row_ok && n + 64 <= p.N) epilogue_prefetch<EPI>(ep, m, n + 32, pre);
-        TS_MARK();
-        if (mode == kStoreDirect) continue;
-        const bool closes_tile = !bf16_out || (c & 32) != 0 || !has_next;
-        if (bf16_out) stage_half_row_bf16(tile, lane, (c >> 5) & 1, v);
-        else stage_row_f32(tile, lane, v);
-        TS_MARK();
-        if (closes_tile) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            const int ncol = bf16_out ? nbeg + (c & ~63) : n;
-            if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, ncol, mrow0);
-            else tma_store_2d(&map_d, tile, ncol, mrow0);
-            bulk_commit();
+          for (int j = 0; j < 32; ++j) r0[j] = tmp[j];
+          if (cpb == 64 && n + 32 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tmp[j] = r1[j];
+            epilogue_slow32(ep, tmp, m, n + 32, mode == kStoreDirect);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r1[j] = tmp[j];
           }
-          sbuf ^= 1;
         }
-        TS_MARK();
+        if (mode == kStoreDirect) continue;
+        if (out_bf16) {
+          stage_half_row_bf16(tile, lane, 0, r0);
+          stage_half_row_bf16(tile, lane, 1, r1);
+        } else {
+          stage_row_f32(tile, lane, r0);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n, mrow0);
+          else tma_store_2d(&map_d, tile, n, mrow0);
+          bulk_commit();
+        }
+        if (!kRes) nbuf = (nbuf + 1 == kBufs) ? 0 : nbuf + 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));  // the leader's MMA thread waits for both CTAs
+        if (kRes && !(p.debug & 1)) {
+          // residual of the next tile -> the other buffer pair, once the stores of the PREVIOUS tile (which
+          // left from that pair) have been read out; this tile's NBLK groups may still be in flight
+          const int tn = t + t_step;
+          if (tn < total_tiles) {
+            if (kResAhead) {
+              bulk_wait_read<NBLK>();
+              res_prefetch(tn, par ^ 1);
+            } else {
+              bulk_wait_read<0>();  // same buffers: this tile's stores must have been read out
+              res_prefetch(tn, 0);
+            }
+          }
+        }
       }
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
@@ -504,9 +506,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-#ifdef DGPT_GEMM_TS
-  if (p.ts && threadIdx.x == 0) p.ts[1500 + blockIdx.x] = clock64() - t_block0;
-#endif
   if (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / retire while the pair's MMAs or arrives are in flight
   if (warp == 1) {
     tc_fence_after();
@@ -569,11 +568,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, int CG>
-static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const TcParams& p, int grid,
-                      cudaStream_t st) {
-  using Cfg = TcCfg<BN, CG>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, CG>;
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS>
+static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
+                      const TcParams& p, int grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, CG, RESBUFS>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, OBF, CG, RESBUFS>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -595,22 +594,7 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (CG == 2) {
-    // a persistent grid must not exceed the number of CTA pairs that can be resident at once (GPCs with an
-    // odd number of usable SMs leave single SMs that cannot host a pair)
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
-      cudaLaunchConfig_t q = cfg;
-      q.gridDim = dim3(2 * 74);
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q) != cudaSuccess || max_clusters <= 0) {
-        cudaGetLastError();
-        max_clusters = 64;
-      }
-      if (getenv("DGPT_GEMM_VERBOSE")) fprintf(stderr, "gemm_tc: max active 2-CTA clusters = %d\n", max_clusters);
-    }
-    if (grid > 2 * max_clusters) cfg.gridDim = dim3((unsigned)(2 * max_clusters));
-  }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mr, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc: launch: %s", cudaGetErrorString(e));
     return DGPT_E_LAUNCH;
@@ -618,9 +602,9 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   return check_launch("gemm_tc");
 }
 
-// Pair tiles (cta_group::2) are opt-in (dgpt_gemm_set_cta_group): on the model's shapes they measured no faster
-// than single-CTA tiles -- the 20-30 us GEMMs are bound by fixed per-launch / per-tile latencies and the
-// epilogue, not by operand delivery -- so the default stays 1.
+// Pair tiles (cta_group::2) are opt-in (dgpt_gemm_set_cta_group / DGPT_GEMM_CTA_GROUP=2): on the model's shapes
+// the single-CTA mainloop already runs at the SM's 64 B/cycle operand-ingest limit and pairs measured at most
+// 5 % faster in the mainloop and slower end to end, so the default stays 1.
 static int g_cta_group = -1;  // -1: not set yet (DGPT_GEMM_CTA_GROUP, default 1)
 void set_gemm_cta_group(int g) { g_cta_group = (g == 2) ? 2 : 1; }
 static int gemm_cta_group() {
@@ -631,16 +615,19 @@ static int gemm_cta_group() {
   return g_cta_group;
 }
 
+struct TcMaps {
+  CUtensorMap a, b, b_half, d, r;
+};
+
 // pair tiles whenever requested and the row-tile count is even, single-CTA tiles otherwise
-template <int BN, int A_MN, int B_MN, int EPI>
-static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb_half, const CUtensorMap& md,
-                      const TcParams& p, int sms, cudaStream_t st) {
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int RESBUFS = 0>
+static int launch_cfg(const TcMaps& m, const TcParams& p, int sms, cudaStream_t st) {
   if (p.cta_group == 2) {
     const int total = (p.m_tiles / 2) * p.n_tiles * p.split_k;
-    return launch_one<BN, A_MN, B_MN, EPI, 2>(ma, mb_half, md, p, 2 * min(total, sms / 2), st);
+    return launch_one<BN, A_MN, B_MN, EPI, OBF, 2, RESBUFS>(m.a, m.b_half, m.d, m.r, p, 2 * min(total, sms / 2), st);
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
-  return launch_one<BN, A_MN, B_MN, EPI, 1>(ma, mb, md, p, min(total, sms), st);
+  return launch_one<BN, A_MN, B_MN, EPI, OBF, 1, RESBUFS>(m.a, m.b, m.d, m.r, p, min(total, sms), st);
 }
 
 int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
@@ -671,90 +658,93 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("gemm_tc: memset: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
   }
   auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-  p.vec_ok = (a->N % 4 == 0) && (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0)) &&
-             (!a->relu_aux || (al16(a->relu_aux) && a->ld_aux % 8 == 0));
-
+  p.vec_ok = (a->N % 4 == 0) && (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0));
+  p.mask_out = a->relu_mask_out;
+  p.mask_in = a->relu_mask_in;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("DGPT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
-#ifdef DGPT_GEMM_TS
-    static long long* ts = nullptr;
-    if (!ts) { cudaMalloc(&ts, 2048 * sizeof(long long)); }
-    cudaMemset(ts, 0, 2048 * sizeof(long long));
-    p.ts = ts;
-#endif
   }
-  CUtensorMap ma, mb, md;
+  TcMaps mp;
   int rc;
-  if (a_mn) rc = make_tmap_bf16_2d(&ma, a->A, a->M, a->K, a->lda, 64);
-  else rc = make_tmap_bf16_2d(&ma, a->A, a->K, a->M, a->lda, TBM);
+  if (a_mn) rc = make_tmap_bf16_2d(&mp.a, a->A, a->M, a->K, a->lda, 64);
+  else rc = make_tmap_bf16_2d(&mp.a, a->A, a->K, a->M, a->lda, TBM);
   if (rc) return rc;
-  CUtensorMap mb_half;  // B as loaded by one CTA of a pair: half of the tile's rows
-  if (b_mn) rc = make_tmap_bf16_2d(&mb, a->B, a->N, a->K, a->ldb, 64);
-  else rc = make_tmap_bf16_2d(&mb, a->B, a->K, a->N, a->ldb, BN);
+  // b_half: B as loaded by one CTA of a pair (half of the tile's rows)
+  if (b_mn) rc = make_tmap_bf16_2d(&mp.b, a->B, a->N, a->K, a->ldb, 64);
+  else rc = make_tmap_bf16_2d(&mp.b, a->B, a->K, a->N, a->ldb, BN);
   if (rc) return rc;
-  if (b_mn) mb_half = mb;
-  else if ((rc = make_tmap_bf16_2d(&mb_half, a->B, a->K, a->N, a->ldb, BN / 2))) return rc;
+  if (b_mn) mp.b_half = mp.b;
+  else if ((rc = make_tmap_bf16_2d(&mp.b_half, a->B, a->K, a->N, a->ldb, BN / 2))) return rc;
   p.cta_group = (gemm_cta_group() == 2 && m_tiles % 2 == 0) ? 2 : 1;
   // output through TMA when its pitch allows it (always true for the model's buffers)
   const int desz = a->d_dtype == DGPT_F32 ? 4 : 2;
   p.store_mode = kStoreDirect;
   if (al16(a->D) && ((int64_t)a->ldd * desz) % 16 == 0) {
-    rc = make_tmap_2d(&md, a->D, a->d_dtype, a->N, a->M, a->ldd, 128 / desz, 32);
+    rc = make_tmap_2d(&mp.d, a->D, a->d_dtype, a->N, a->M, a->ldd, 128 / desz, 32);
     if (rc) return rc;
     p.store_mode = (p.ep.atomic || a->accumulate) ? kStoreTmaAdd : kStoreTma;
   } else {
-    md = ma;
+    mp.d = mp.a;
   }
-  if (p.store_mode == kStoreDirect || a->D2 || (a->residual && a->relu_aux)) p.vec_ok = 0;  // everything through the compact element-wise path
+  mp.r = mp.a;
 
-  // epilogue specialisation: the combinations the model uses get their own instantiation, the rest run
-  // the generic (run-time flag) kernel
-  const int epi = (a->bias ? kEpiBias : 0) | (a->relu ? kEpiRelu : 0) | (a->relu_aux ? kEpiAux : 0) |
-                  (a->dropout_p > 0.f ? kEpiDrop : 0) | (a->residual ? kEpiRes : 0);
-#ifdef DGPT_GEMM_TS
-  {  // debug build: run synchronously and print the stamp deltas of the first three tiles of block 0
-    int rcx = (BN == 256) ? launch_cfg<256, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st)
-                          : launch_cfg<128, 0, 0, kEpiBias | kEpiRelu>(ma, mb, mb_half, md, p, sms, st);
-    cudaStreamSynchronize(st);
-    long long h[2048];
-    cudaMemcpy(h, p.ts, sizeof(h), cudaMemcpyDeviceToHost);
-    {
-      printf("block durations (cycles):");
-      for (int i = 0; i < 148; ++i) printf(" %lld", h[1500 + i]);
-      printf("\n");
-    }
-    for (int t = 0; t < 3; ++t) {
-      printf("tile %d:", t);
-      for (int i = 1; i < 48 && h[t * 64 + i]; ++i) printf(" %lld", h[t * 64 + i] - h[t * 64 + i - 1]);
-      printf("\nblock durations (cycles):");
-      for (int i = 0; i < 148; ++i) printf(" %lld", h[1500 + i]);
-      printf("\n");
-    }
-    fflush(stdout);
-    return rcx;
+  // Epilogue specialisation: the combinations the model uses get their own (fast-path) instantiation, the
+  // rest run the generic element-wise kernel.  Fast path needs TMA-addressable output, vector-aligned
+  // operands, no second output, no saved-activation mask, and (bias / residual) no split-K.
+  int epi = (a->bias ? kEpiBias : 0) | (a->relu ? kEpiRelu : 0) | (a->relu_aux ? kEpiAux : 0) |
+            (a->dropout_p > 0.f ? kEpiDrop : 0) | (a->residual ? kEpiRes : 0) | (a->relu_mask_in ? kEpiMaskIn : 0) |
+            (a->relu_mask_out ? kEpiMaskOut : 0);
+  const int obf = a->d_dtype == DGPT_BF16 ? 1 : 0;
+  if (a->relu_mask_in || a->relu_mask_out) {
+    DGPT_REQUIRE(p.store_mode != kStoreDirect && p.vec_ok && !a->D2 && !a->relu_aux && a->N % 64 == 0 && obf && p.split_k == 1,
+                 "gemm(bf16): relu_mask_in/out need a bf16, 16-byte aligned output with N %% 64 == 0 and no split-K");
+    DGPT_REQUIRE(epi == kEpiMaskIn || epi == (kEpiBias | kEpiRelu | kEpiMaskOut),
+                 "gemm(bf16): relu_mask_out goes with bias + ReLU only, relu_mask_in with a plain epilogue only");
   }
-#endif
-#define TC_EPI(BN_, A_, B_, E_) \
-  if (epi == (E_)) return launch_cfg<BN_, A_, B_, (E_)>(ma, mb, mb_half, md, p, sms, st);
-#define TC_DISPATCH(BN_)                                                          \
-  if (BN == BN_) {                                                                \
-    if (!a_mn && !b_mn) {                                                         \
-      TC_EPI(BN_, 0, 0, 0)                                                        \
-      TC_EPI(BN_, 0, 0, kEpiBias)                                                 \
-      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu)                                      \
-      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRes)                                       \
-      TC_EPI(BN_, 0, 0, kEpiBias | kEpiDrop | kEpiRes)                            \
-      return launch_cfg<BN_, 0, 0, -1>(ma, mb, mb_half, md, p, sms, st);                  \
-    }                                                                             \
-    if (!a_mn && b_mn) {                                                          \
-      TC_EPI(BN_, 0, 1, 0)                                                        \
-      TC_EPI(BN_, 0, 1, kEpiAux)                                                  \
-      return launch_cfg<BN_, 0, 1, -1>(ma, mb, mb_half, md, p, sms, st);                  \
-    }                                                                             \
-    TC_EPI(BN_, 1, 1, 0)                                                          \
-    return launch_cfg<BN_, 1, 1, -1>(ma, mb, mb_half, md, p, sms, st);                    \
+  if (p.store_mode == kStoreDirect || !p.vec_ok || a->D2 || a->relu_aux) epi = -1;
+  if (epi > 0 && (epi & (kEpiBias | kEpiRes)) && p.split_k > 1) epi = -1;
+  if (epi >= 0 && (epi & kEpiRes)) {
+    if (BN != 128 || obf) {
+      epi = -1;  // the TMA-fed residual path is instantiated for 128-column tiles with fp32 output
+    } else {
+      DGPT_REQUIRE(a->ldr % 4 == 0, "gemm(bf16): residual pitch");
+      if ((rc = make_tmap_2d(&mp.r, a->residual, DGPT_F32, a->N, a->M, a->ldr, 32, 32))) return rc;
+    }
+  }
+  // residual staging buffers per epilogue warp (see TcCfg)
+  static int res_bufs_env = -1;
+  if (res_bufs_env < 0) { const char* e = getenv("DGPT_GEMM_RES_BUFS"); res_bufs_env = e ? atoi(e) : 0; }
+  const int res_bufs = res_bufs_env == 4 ? 4 : 2;  // measured: 2 is never slower (DGPT_GEMM_RES_BUFS=4 for experiments)
+#define TC_EPI(BN_, A_, B_, E_, O_) \
+  if (epi == (E_) && obf == (O_)) return launch_cfg<BN_, A_, B_, (E_), O_>(mp, p, sms, st);
+#define TC_DISPATCH(BN_)                                                              \
+  if (BN == BN_) {                                                                    \
+    if (!a_mn && !b_mn) {                                                             \
+      TC_EPI(BN_, 0, 0, 0, 1)                                                         \
+      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu, 1)                                       \
+      TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu | kEpiMaskOut, 1)                         \
+      if (BN_ == 128 && epi >= 0 && (epi & kEpiRes)) {                                \
+        const bool ahead = res_bufs == 4;                                             \
+        if (epi == (kEpiBias | kEpiRes))                                              \
+          return ahead ? launch_cfg<128, 0, 0, kEpiBias | kEpiRes, 0, 4>(mp, p, sms, st)              \
+                       : launch_cfg<128, 0, 0, kEpiBias | kEpiRes, 0, 2>(mp, p, sms, st);             \
+        if (epi == (kEpiBias | kEpiDrop | kEpiRes))                                   \
+          return ahead ? launch_cfg<128, 0, 0, kEpiBias | kEpiDrop | kEpiRes, 0, 4>(mp, p, sms, st)   \
+                       : launch_cfg<128, 0, 0, kEpiBias | kEpiDrop | kEpiRes, 0, 2>(mp, p, sms, st);  \
+        epi = -1;                                                                     \
+      }                                                                               \
+      return launch_cfg<BN_, 0, 0, -1, 0>(mp, p, sms, st);                            \
+    }                                                                                 \
+    if (!a_mn && b_mn) {                                                              \
+      TC_EPI(BN_, 0, 1, 0, 1)                                                         \
+      TC_EPI(BN_, 0, 1, 0, 0)                                                         \
+      TC_EPI(BN_, 0, 1, kEpiMaskIn, 1)                                                \
+      return launch_cfg<BN_, 0, 1, -1, 0>(mp, p, sms, st);                            \
+    }                                                                                 \
+    TC_EPI(BN_, 1, 1, 0, 0)                                                           \
+    return launch_cfg<BN_, 1, 1, -1, 0>(mp, p, sms, st);                              \
   }
   TC_DISPATCH(128)
   TC_DISPATCH(256)

@@ -137,6 +137,9 @@ class Runner:
     def _gemm(self, *a, **k):
         return ops.raw_gemm(*a, **k)
 
+    def _use_relu_mask(self, F):
+        return self.mode == "bf16" and F % 64 == 0
+
     # ------------------------------------------------------------------ #
     # forward
     # ------------------------------------------------------------------ #
@@ -229,8 +232,11 @@ class Runner:
                 out = self.buf(tag("x2"), (M, C), torch.float32)
                 self._gemm(b, self.w(L["ffn"][1]), out, bias=self.f(L["ffn"][2]), relu=True)
             else:
-                h = self.buf(tag("h"), (M, self.f(L["ffn"][1]).shape[0]))
-                self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True)
+                F = self.f(L["ffn"][1]).shape[0]
+                h = self.buf(tag("h"), (M, F))
+                # tensor mode: the GEMM also writes the ReLU bit mask its dgrad twin applies (1/16 of re-reading h)
+                hmask = self.buf(tag("hmask"), ((F // 32) * M,), torch.int32) if save and self._use_relu_mask(F) else None
+                self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True, relu_mask_out=hmask)
                 out = self.buf(tag("x2"), (M, C), torch.float32)
                 self._gemm(h, self.w(L["ffn"][3]), out, bias=self.f(L["ffn"][4]),
                            dropout=self._drop(L["p"], 4 * li + 2, training), residual=x1 if L["residual"] else None)
@@ -321,7 +327,11 @@ class Runner:
         if li == len(self.spec["layers"]) - 1:  # other layers: fused into the LN1 backward of layer li+1
             ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
         dh = self.buf("dh", (M, F))
-        self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN, relu_aux=h)
+        if self._use_relu_mask(F):
+            self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN,
+                       relu_mask_in=self.buf(tag("hmask"), ((F // 32) * M,), torch.int32))
+        else:
+            self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN, relu_aux=h)
         # ---- FFN1: h = relu(xn2 W1^T + b1) ----
         self._gemm(dh, xn2, self.g(L["ffn"][1]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                    split_k=self._splits(F, C, M, sm))

@@ -60,8 +60,13 @@ class Dropout:
 # raw kernel launches
 # --------------------------------------------------------------------------- #
 def raw_gemm(A, B, out, *, a_major=MAJOR_K, b_major=MAJOR_K, M=None, N=None, K=None, bias=None, relu=False,
-             relu_aux=None, dropout=None, residual=None, out2=None, accumulate=False, split_k=1):
-    """out[M,N] = epilogue(A . B^T); see dgpt_gemm in include/drakegpt_b200.h."""
+             relu_aux=None, dropout=None, residual=None, out2=None, accumulate=False, split_k=1,
+             relu_mask_out=None, relu_mask_in=None):
+    """out[M,N] = epilogue(A . B^T); see dgpt_gemm in include/drakegpt_b200.h.
+
+    relu_mask_out / relu_mask_in: int32 tensors of (N // 32) * M words (tensor mode): the ReLU bit mask the
+    forward GEMM writes and the dgrad GEMM applies.
+    """
     _need_cuda(A, B, out)
     if M is None:
         M = A.shape[0] if a_major == MAJOR_K else A.shape[1]
@@ -84,6 +89,10 @@ def raw_gemm(A, B, out, *, a_major=MAJOR_K, b_major=MAJOR_K, M=None, N=None, K=N
     a.ldr = residual.stride(0) if residual is not None else 0
     a.ld_aux = relu_aux.stride(0) if relu_aux is not None else 0
     a.relu, a.accumulate, a.split_k = int(relu), int(accumulate), int(split_k)
+    for mk in (relu_mask_out, relu_mask_in):
+        if mk is not None and (mk.dtype != torch.int32 or mk.numel() < (N // 32) * M or not mk.is_contiguous()):
+            raise _lib.KernelError("gemm: relu masks are contiguous int32 tensors of (N // 32) * M words")
+    a.relu_mask_out, a.relu_mask_in = _p(relu_mask_out), _p(relu_mask_in)
     if dropout is not None and dropout.p > 0.0:
         a.dropout_p, a.seed, a.site, a.seed_dev = dropout.p, dropout.seed, dropout.site, _p(dropout.seed_dev)
     check(_lib.lib().dgpt_gemm(C.byref(a), _stream()), "dgpt_gemm")

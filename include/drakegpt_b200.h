@@ -132,6 +132,12 @@ typedef struct dgpt_gemm_args {
   uint32_t site;
   uint64_t seed;
   const uint64_t* seed_dev; /* optional device-side seed offset            */
+  /* ReLU bit masks (tensor mode only; bf16 D, N % 64 == 0): word [(n / 32) * M + m] holds, in bit n % 32,
+   * whether the pre-activation (m, n) was positive.  The forward GEMM (bias + relu) writes it, the dgrad
+   * GEMM zeroes its output where the bit is clear -- 1/16 of the bytes of re-reading the bf16 activation
+   * (src/model_component.py:321-322: Linear -> ReLU, and its autograd backward). */
+  uint32_t* relu_mask_out;
+  const uint32_t* relu_mask_in;
 } dgpt_gemm_args;
 int dgpt_gemm(const dgpt_gemm_args* a, void* stream);
 /* Tensor-mode tiling knob: 1 (default) = one CTA per 128-row tile; 2 = CTA pairs (thread-block cluster of 2,

@@ -155,6 +155,53 @@ def test_gemm_tcgen05_epilogue_and_splitk():
     torch.testing.assert_close(gacc.cpu(), 1 + X.float().t() @ Y.float(), rtol=1e-3, atol=5e-2)
 
 
+@pytest.mark.parametrize("M", [256, 200, 16384 + 96])
+def test_gemm_tcgen05_residual_by_tma(M):
+    """bias (+ dropout) + fp32 residual without a second output: the residual block reaches the epilogue by TMA
+    (several tiles per CTA at the large M, ragged last row tile)."""
+    g = torch.Generator().manual_seed(5 + M)
+    N, K, p, seed, site = 384, 192, 0.2, 1234, 9
+    A, Bm = torch.randn(M, K, generator=g).bfloat16(), torch.randn(N, K, generator=g).bfloat16()
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    acc = A.float() @ Bm.float().t()
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.raw_gemm(A.to(DEV), Bm.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV))
+    torch.testing.assert_close(out.cpu(), acc + bias + res, rtol=1e-3, atol=5e-2)
+    if M <= 256:
+        keep = _keep_mask((M, N), seed, site, p)
+        out.fill_(float("nan"))
+        ops.raw_gemm(A.to(DEV), Bm.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV), dropout=ops.Dropout(p, seed, site))
+        torch.testing.assert_close(out.cpu(), (acc + bias) * keep / (1 - p) + res, rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("M,N", [(256, 256), (200, 1536), (384, 192)])
+def test_gemm_tcgen05_relu_bit_masks(M, N):
+    """Forward GEMM writes the ReLU bit mask, the dgrad GEMM applies it (== masking with the saved activation)."""
+    g = torch.Generator().manual_seed(31 + N)
+    K = 128
+    A, Bm = torch.randn(M, K, generator=g).bfloat16(), torch.randn(N, K, generator=g).bfloat16()
+    bias = torch.randn(N, generator=g)
+    pre = A.float() @ Bm.float().t() + bias
+    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    mask = torch.zeros((N // 32) * M, device=DEV, dtype=torch.int32)
+    ops.raw_gemm(A.to(DEV), Bm.to(DEV), h, bias=bias.to(DEV), relu=True, relu_mask_out=mask)
+    torch.testing.assert_close(h.float().cpu(), torch.relu(pre), rtol=1e-2, atol=1e-1)
+    bits = (mask.cpu().view(N // 32, M, 1) >> torch.arange(32, dtype=torch.int32).view(1, 1, 32)) & 1
+    got = bits.permute(1, 0, 2).reshape(M, N).bool()
+    want = pre > 0
+    # only values within rounding distance of zero may differ (tensor-core summation order)
+    assert ((got != want) & (pre.abs() > 1e-2)).sum() == 0
+    # dgrad twin: dY . W masked by the bits   (W [N, K] read MN-major as the B operand of a [M, N] x [N, K] product)
+    G = torch.randn(M, K, generator=g).bfloat16()
+    W2 = torch.randn(K, N, generator=g).bfloat16()  # nn.Linear(N -> K) weight: (out=K, in=N)
+    d = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.raw_gemm(G.to(DEV), W2.to(DEV), d, b_major=MAJOR_MN, relu_mask_in=mask)
+    ref = (G.float() @ W2.float()) * got
+    torch.testing.assert_close(d.float().cpu(), ref, rtol=1e-2, atol=1e-1)
+    with pytest.raises(_lib.KernelError):
+        ops.raw_gemm(G.float().to(DEV), W2.float().to(DEV), torch.empty(M, N, device=DEV), b_major=MAJOR_MN, relu_mask_in=mask)
+
+
 def test_layernorm_fwd_bwd():
     g = torch.Generator().manual_seed(2)
     for M, C in [(64, 32), (33, 384), (5, 50)]:

@@ -45,11 +45,11 @@ def make(name):
     out = torch.zeros(M, N, device=dev, dtype=odt)
     kw = {}
     if epi == "bias_relu":
-        kw = dict(bias=torch.zeros(N, device=dev), relu=True)
+        kw = dict(bias=torch.zeros(N, device=dev), relu=True, relu_mask_out=torch.zeros((N // 32) * M, device=dev, dtype=torch.int32))
     elif epi == "bias_drop_res":
         kw = dict(bias=torch.zeros(N, device=dev), residual=torch.zeros(M, N, device=dev), dropout=ops.Dropout(0.2, 1, 1))
     elif epi == "relu_aux":
-        kw = dict(relu_aux=torch.randn(M, N, device=dev).bfloat16())
+        kw = dict(relu_mask_in=torch.randint(-2**31, 2**31 - 1, ((N // 32) * M,), device=dev, dtype=torch.int32))
     elif epi == "splitk":
         kw = dict(accumulate=True, split_k=splits(M, N, K))
     return lambda: ops.raw_gemm(A, B, out, a_major=am, b_major=bm, **kw)
