@@ -186,15 +186,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           sum += v;
           e[j] = v;
         }
-        if (p.thr) {
+        if (p.thr) {  // the 32 keys of this chunk are one mask group (T % 32 == 0)
+          const DropGroup g = dropout_group(seed, p.site, (base + c) >> 5);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const u32x4 bits = dropout_bits4(seed, p.site, (base + c + 4 * j) >> 2);
-            if (bits.x < p.thr) e[4 * j] = 0.f;
-            if (bits.y < p.thr) e[4 * j + 1] = 0.f;
-            if (bits.z < p.thr) e[4 * j + 2] = 0.f;
-            if (bits.w < p.thr) e[4 * j + 3] = 0.f;
-          }
+          for (int j = 0; j < 32; ++j)
+            if (dropout_word(g, j) < p.thr) e[j] = 0.f;
         }
       }
       store_row32_sw128(sP, row, c, e);
@@ -249,28 +245,21 @@ __device__ __forceinline__ void bwd_chunk(const AttnTcP& p, uint32_t lane_addr_s
   tmem_ld32(lane_addr_dp + k0, dp);
   tmem_ld_wait();
   float pd[32], ds[32];
+  DropGroup g = {0u, 0u};
+  if (DROP) g = dropout_group(seed, p.site, (base + k0) >> 5);  // the chunk's 32 keys are one mask group
 #pragma unroll
-  for (int t4 = 0; t4 < 8; ++t4) {
-    uint32_t bw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+  for (int t = 0; t < 32; ++t) {
+    float pv = exp2f(__uint_as_float(st[t]) * sc - lse2);
+    if (DIAG) pv = (k0 + t) <= row ? pv : 0.f;
+    float dpv = __uint_as_float(dp[t]);
+    float pdv = pv;
     if (DROP) {
-      const u32x4 bits = dropout_bits4(seed, p.site, (base + k0 + 4 * t4) >> 2);
-      bw[0] = bits.x; bw[1] = bits.y; bw[2] = bits.z; bw[3] = bits.w;
+      const bool keep = dropout_word(g, t) >= p.thr;
+      dpv = keep ? dpv * p.inv_keep : 0.f;
+      pdv = keep ? pv * p.inv_keep : 0.f;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = 4 * t4 + u;
-      float pv = exp2f(__uint_as_float(st[t]) * sc - lse2);
-      if (DIAG) pv = (k0 + t) <= row ? pv : 0.f;
-      float dpv = __uint_as_float(dp[t]);
-      float pdv = pv;
-      if (DROP) {
-        const bool keep = bw[u] >= p.thr;
-        dpv = keep ? dpv * p.inv_keep : 0.f;
-        pdv = keep ? pv * p.inv_keep : 0.f;
-      }
-      pd[t] = pdv;
-      ds[t] = pv * (dpv - Dq) * p.scale;
-    }
+    pd[t] = pdv;
+    ds[t] = pv * (dpv - Dq) * p.scale;
   }
   store_row32_sw128(sPd, row, k0, pd);
   store_row32_sw128(sDs, row, k0, ds);

@@ -59,11 +59,15 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1
 }
 
 // ---------------------------------------------------------------------------
-// Dropout mask: counter-based SplitMix64.  Four consecutive elements [4q, 4q+3] of a
-// dropout site share ONE 64-bit hash (16 bits each), i.e. ~5 integer instructions per
-// element instead of ~25 with Philox4x32-10 -- the mask is regenerated inside the
-// attention and GEMM-epilogue inner loops, so its cost is on the critical path.
-//   state(q) = seed + q * golden + (site+1) * K   (the SplitMix64 stream, offset per site)
+// Dropout mask: counter-based, two levels.  The mask is regenerated inside the attention and
+// GEMM-epilogue inner loops (forward AND backward), so its cost is on the critical path:
+//   * one SplitMix64 hash per GROUP of 32 consecutive elements:
+//       (s0, s1) = mix64(seed + group * golden + (site + 1) * K)
+//   * one 32-bit multiply-add per element e of the group:
+//       word(e) = (e odd ? s1 : s0) * MUL[e] + ADD[e]      (MUL odd: a bijection of the group hash)
+//     keep iff word(e) >= threshold, P(drop) = threshold / 2^32.
+// ~3 integer instructions per element when a thread walks whole groups (MUL / ADD fold into
+// immediates), against ~8 with one 64-bit hash per four elements and ~25 with Philox4x32-10.
 // ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -71,17 +75,40 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
+struct DropGroup {
+  uint32_t s0, s1;
+};
+__host__ __device__ __forceinline__ DropGroup dropout_group(uint64_t seed, uint32_t site, uint64_t group) {
+  const uint64_t h = mix64(seed + group * 0x9E3779B97F4A7C15ull + (uint64_t)(site + 1u) * 0xD1B54A32D192ED03ull);
+  return DropGroup{(uint32_t)h, (uint32_t)(h >> 32)};
+}
+__host__ __device__ constexpr uint32_t drop_mul(uint32_t e) {
+  uint32_t x = (e + 1u) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+  return x | 1u;
+}
+__host__ __device__ constexpr uint32_t drop_add(uint32_t e) {
+  uint32_t x = (e + 33u) * 0xC2B2AE3Du;
+  x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 15;
+  return x;
+}
+// uniform 32-bit word of element e (0..31) of the group
+__host__ __device__ __forceinline__ uint32_t dropout_word(const DropGroup& g, uint32_t e) {
+  return ((e & 1u) ? g.s1 : g.s0) * drop_mul(e) + drop_add(e);
+}
+
+// the four words of elements [4 quad, 4 quad + 3] (any quad; one group hash per call)
 __host__ __device__ __forceinline__ u32x4 dropout_bits4(uint64_t seed, uint32_t site, uint64_t quad) {
-  const uint64_t h = mix64(seed + quad * 0x9E3779B97F4A7C15ull + (uint64_t)(site + 1u) * 0xD1B54A32D192ED03ull);
-  return u32x4{(uint32_t)(h & 0xFFFFu), (uint32_t)((h >> 16) & 0xFFFFu), (uint32_t)((h >> 32) & 0xFFFFu),
-               (uint32_t)(h >> 48)};
+  const DropGroup g = dropout_group(seed, site, quad >> 3);
+  const uint32_t e0 = ((uint32_t)quad & 7u) * 4u;
+  return u32x4{dropout_word(g, e0), dropout_word(g, e0 + 1u), dropout_word(g, e0 + 2u), dropout_word(g, e0 + 3u)};
 }
 
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-  // keep iff 16-bit lane >= threshold; P(drop) = threshold / 65536 (0 = dropout off)
-  double t = (double)p * 65536.0 + 0.5;
+  // keep iff word >= threshold; P(drop) = threshold / 2^32 (0 = dropout off)
+  double t = (double)p * 4294967296.0 + 0.5;
   if (t < 0.0) t = 0.0;
-  if (t > 65535.0) t = 65535.0;
+  if (t > 4294967295.0) t = 4294967295.0;
   return (uint32_t)t;
 }
 
@@ -91,8 +118,7 @@ __host__ __device__ __forceinline__ uint32_t pick4(const u32x4& r, int lane) {
 
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t index,
                                                       uint32_t threshold) {
-  const u32x4 r = dropout_bits4(seed, site, index >> 2);
-  return pick4(r, (int)(index & 3)) >= threshold;
+  return dropout_word(dropout_group(seed, site, index >> 5), (uint32_t)index & 31u) >= threshold;
 }
 
 // ---------------------------------------------------------------------------

@@ -104,14 +104,21 @@ __device__ __forceinline__ void epi_math32(const Epilogue& e, int m, int n, uint
     for (int j = 0; j < 32; ++j) r[j] = ((mask_in >> j) & 1u) ? r[j] : 0u;
   }
   if (EPI & kEpiDrop) {
-    const uint64_t q0 = ((uint64_t)m * (uint64_t)e.N + (uint64_t)n) >> 2;
+    const uint64_t i0 = (uint64_t)m * (uint64_t)e.N + (uint64_t)n;
+    if ((e.N & 31) == 0) {  // the 32 columns are one mask group: one hash, then a multiply-add per element
+      const DropGroup g = dropout_group(e.seed, e.site, i0 >> 5);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const u32x4 b = dropout_bits4(e.seed, e.site, q0 + j);
-      r[4 * j] = b.x >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j]) * e.inv_keep) : 0u;
-      r[4 * j + 1] = b.y >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 1]) * e.inv_keep) : 0u;
-      r[4 * j + 2] = b.z >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 2]) * e.inv_keep) : 0u;
-      r[4 * j + 3] = b.w >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 3]) * e.inv_keep) : 0u;
+      for (int j = 0; j < 32; ++j)
+        r[j] = dropout_word(g, j) >= e.thr ? __float_as_uint(__uint_as_float(r[j]) * e.inv_keep) : 0u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const u32x4 b = dropout_bits4(e.seed, e.site, (i0 >> 2) + j);
+        r[4 * j] = b.x >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j]) * e.inv_keep) : 0u;
+        r[4 * j + 1] = b.y >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 1]) * e.inv_keep) : 0u;
+        r[4 * j + 2] = b.z >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 2]) * e.inv_keep) : 0u;
+        r[4 * j + 3] = b.w >= e.thr ? __float_as_uint(__uint_as_float(r[4 * j + 3]) * e.inv_keep) : 0u;
+      }
     }
   }
   if (EPI & kEpiRes) {
