@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("ldr", C.c_int32), ("ld_aux", C.c_int32),
         ("relu", C.c_int32), ("accumulate", C.c_int32), ("split_k", C.c_int32),
         ("dropout_p", C.c_float), ("site", C.c_uint32), ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
-        ("relu_mask_out", C.c_void_p), ("relu_mask_in", C.c_void_p),
+        ("relu_mask_out", C.c_void_p), ("relu_mask_in", C.c_void_p), ("a_colsum", C.c_void_p),
     ]
 
 

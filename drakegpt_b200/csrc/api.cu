@@ -43,8 +43,8 @@ int dgpt_gemm(const dgpt_gemm_args* a, void* stream) {
     DGPT_REQUIRE(!a->relu && !a->relu_aux && a->dropout_p == 0.f && a->d_dtype == DGPT_F32 && !a->D2,
                  "gemm: split_k>1 only with a linear epilogue and fp32 D");
   cudaStream_t st = (cudaStream_t)stream;
-  DGPT_REQUIRE(a->in_dtype == DGPT_BF16 || (!a->relu_mask_in && !a->relu_mask_out),
-               "gemm: relu_mask_in/out are tensor-mode (bf16) features");
+  DGPT_REQUIRE(a->in_dtype == DGPT_BF16 || (!a->relu_mask_in && !a->relu_mask_out && !a->a_colsum),
+               "gemm: relu_mask_in/out and a_colsum are tensor-mode (bf16) features");
   if (a->in_dtype == DGPT_F32) return launch_gemm_f32(a, st);
   if (a->in_dtype == DGPT_BF16) return launch_gemm_tc(a, st);
   set_error("gemm: unknown in_dtype %d", a->in_dtype);

@@ -42,6 +42,7 @@ struct TcParams {
   int debug;       // DGPT_GEMM_DEBUG: 1 = epilogue skipped, 2 = no TMA loads / MMAs (timing experiments only)
   uint32_t* mask_out;        // ReLU bit mask written by the forward GEMM  [(n / 32) * M + m]
   const uint32_t* mask_in;   // ... and applied by the dgrad GEMM
+  float* a_colsum;           // out[m] += sum_k A[m, k]  (bias gradient riding on the wgrad GEMM, CS instantiations)
   Epilogue ep;
 };
 
@@ -54,7 +55,7 @@ enum { kEpiBias = 1, kEpiRelu = 2, kEpiAux = 4, kEpiDrop = 8, kEpiRes = 16, kEpi
 // 4 buffers per warp = the next tile's residual is fetched while this tile's stores drain (short-K GEMMs, whose
 // epilogue is the critical path; ring of 3 stages); 2 buffers = fetched once this tile's stores have been read
 // (long-K GEMMs: the epilogue warps have slack, the mainloop wants the 5-stage ring).
-template <int BN, int CG, int RESBUFS>
+template <int BN, int CG, int RESBUFS, int CS = 0>
 struct TcCfg {
   static constexpr int kBBytes = (BN / CG) * TBK * 2;
   static constexpr int kStageBytes = TBM * TBK * 2 + kBBytes;
@@ -64,7 +65,8 @@ struct TcCfg {
   static constexpr int kBarBytes = 512;
   static constexpr int kRing = kSmemMax - kStagingBytes - kBiasBytes - kBarBytes;
   static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512 (powers of two)
+  static constexpr int kTmemCols = CS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);  // powers of two; CS: + 2 x 16 column-sum columns
+  static_assert(!CS || 2 * BN + 32 <= 512, "no TMEM room for the column-sum accumulators");
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
   static_assert(kStages >= 3, "shared-memory ring too shallow");
 };
@@ -184,18 +186,25 @@ __device__ __forceinline__ void stage_half_row_bf16(uint8_t* tile, int row, int 
   }
 }
 
+// every split owns at least one k-block (launch_gemm_tc re-derives split_k from kb_per_split)
+__device__ __forceinline__ bool kb_nonempty(const TcParams& p, int ks) { return ks * p.kb_per_split < p.kb_total; }
+
 // --------------------------------------------------------------------------
 // the kernel
 //   EPI  : compile-time epilogue feature mask (fast path), or -1 = generic element-wise epilogue
 //   OBF  : output element type of the fast path (1 = bf16, 0 = fp32); ignored when EPI < 0
 // --------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS>
+// CS = 1 (wgrad form: A MN-major, plain fp32 epilogue, CG = 1): the column sums of the stored A matrix
+// (= row sums of the logical A: sum_k A[m, k], the bias gradient when A = dY^T) ride on the tensor core as
+// one extra N = 16 MMA per k-step against an all-ones B tile -- no separate pass over dY.
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r, TcParams p) {
   constexpr bool kRes = EPI >= 0 && (EPI & kEpiRes) != 0;
   static_assert(kRes == (RESBUFS != 0), "RESBUFS goes with the residual epilogues");
-  using Cfg = TcCfg<BN, CG, RESBUFS>;
+  using Cfg = TcCfg<BN, CG, RESBUFS, CS>;
+  static_assert(!CS || (CG == 1 && EPI == 0), "column sums: single-CTA tiles, plain epilogue");
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = TBM * TBK * 2;
   constexpr int kBBytes = Cfg::kBBytes;
@@ -229,6 +238,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
+  }
+  if (CS && warp >= 2) {
+    // all-ones bf16 tile (8 rows x 128 B, every layout of it is the same tile) in the unused bias region
+    uint32_t* ones = reinterpret_cast<uint32_t*>(bias_s);
+    for (int i = threadIdx.x - 64; i < 256; i += 256) ones[i] = 0x3F803F80u;
+    fence_proxy_async();  // generic-proxy writes -> visible to the MMA's async-proxy reads (after the barrier below)
   }
   if (CG == 2) {  // both CTAs of the pair have initialised their barriers before the paired TMEM allocation
     __syncthreads();
@@ -313,6 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int t = t_first; t < total_tiles; t += t_step) {
         const int ks = t / tiles_mn;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const bool cs_tile = CS && ((t - ks * tiles_mn) % p.n_tiles) == 0;  // column sums: once per row tile
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -333,6 +349,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t db = db0 + (uint64_t)(k * (B_MN ? 128 : 2));
               if (CG == 1) tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
               else tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CS && cs_tile) {
+                // ones tile: K-major, N = 16 rows as two aliased 8-row groups (SBO = 0), 32 bytes per UMMA_K
+                const uint64_t d1 = make_smem_desc_sw128(smem_u32(bias_s), 16, 0) + (uint64_t)(k * 2);
+                tc_mma_bf16(tmem_base + (uint32_t)(2 * BN + acc * 16), da, d1, make_idesc_bf16(TBM, 16, A_MN, 0),
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+              }
             }
             if (CG == 1) tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
             else tc_commit_2sm(&empty_bar[s]);      // ... in both CTAs of the pair
@@ -486,6 +508,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (!kRes) nbuf = (nbuf + 1 == kBufs) ? 0 : nbuf + 1;
       }
+      if (CS && n0 == 0 && half == 0 && mrow0 < p.M) {
+        const float cs = __uint_as_float(tmem_ld1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * BN + acc * 16)));
+        tmem_ld_wait();
+        if (m < p.M && kb_nonempty(p, ks)) atomicAdd(p.a_colsum + m, cs);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -575,11 +602,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS>
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS = 0>
 static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
                       const TcParams& p, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, CG, RESBUFS>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, OBF, CG, RESBUFS>;
+  using Cfg = TcCfg<BN, CG, RESBUFS, CS>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, OBF, CG, RESBUFS, CS>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -648,7 +675,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   // 128 x 256 tiles ingest 25 % fewer operand bytes per MMA cycle than 128 x 128; a ragged last column
   // tile (N = 1152 -> 4.5 tiles) costs less than that as soon as N >= 1024 (TMA zero-fills, the store clips)
   int BN = 256;
-  if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024)) BN = 128;
+  if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024) || a->a_colsum) BN = 128;
   if (BN == 256 && m_tiles * ceil_div(a->N, 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
   const int n_tiles = ceil_div(a->N, BN);
   TcParams p;
@@ -668,6 +695,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   p.vec_ok = (a->N % 4 == 0) && (!a->bias || al16(a->bias)) && (!a->residual || (al16(a->residual) && a->ldr % 4 == 0));
   p.mask_out = a->relu_mask_out;
   p.mask_in = a->relu_mask_in;
+  p.a_colsum = a->a_colsum;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("DGPT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -710,6 +738,8 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     DGPT_REQUIRE(epi == kEpiMaskIn || epi == (kEpiBias | kEpiRelu | kEpiMaskOut),
                  "gemm(bf16): relu_mask_out goes with bias + ReLU only, relu_mask_in with a plain epilogue only");
   }
+  DGPT_REQUIRE(!a->a_colsum || (a_mn && b_mn && p.store_mode != kStoreDirect && p.vec_ok && !a->D2),
+               "gemm(bf16): a_colsum rides on MN-major (wgrad) GEMMs with a 16-byte aligned fp32 output");
   if (p.store_mode == kStoreDirect || !p.vec_ok || a->D2 || a->relu_aux) epi = -1;
   if (epi > 0 && (epi & (kEpiBias | kEpiRes)) && p.split_k > 1) epi = -1;
   if (epi >= 0 && (epi & kEpiRes)) {
@@ -749,6 +779,11 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
       TC_EPI(BN_, 0, 1, 0, 0)                                                         \
       TC_EPI(BN_, 0, 1, kEpiMaskIn, 1)                                                \
       return launch_cfg<BN_, 0, 1, -1, 0>(mp, p, sms, st);                            \
+    }                                                                                 \
+    if (a->a_colsum) {                                                                \
+      DGPT_REQUIRE(BN_ == 128 && epi == 0 && obf == 0, "gemm(bf16): a_colsum needs the plain fp32 wgrad form");   \
+      const int total = p.m_tiles * p.n_tiles * p.split_k;                            \
+      return launch_one<128, 1, 1, 0, 0, 1, 0, 1>(mp.a, mp.b, mp.d, mp.r, p, min(total, sms), st);               \
     }                                                                                 \
     TC_EPI(BN_, 1, 1, 0, 0)                                                           \
     return launch_cfg<BN_, 1, 1, -1, 0>(mp, p, sms, st);                              \

@@ -266,9 +266,11 @@ class Runner:
         dl = self.buf("dlogits", (M, (V + 7) // 8 * 8), self.at, zero=True)
         x_last = self._x_last
         # lm_head: dW = dl^T x, db = colsum(dl), dx = dl W
+        tc = self.mode == "bf16"  # tensor mode: bias gradients ride on the wgrad GEMMs (a_colsum)
         self._gemm(dl, x_last, self.g(sp["lm"][0]), a_major=MAJOR_MN, b_major=MAJOR_MN, M=V, N=C, K=M,
-                   accumulate=True, split_k=self._splits(V, C, M, sm))
-        ops.raw_colsum(dl, self.g(sp["lm"][1]), accumulate=True, M=M, N=V)
+                   accumulate=True, split_k=self._splits(V, C, M, sm), a_colsum=self.g(sp["lm"][1]) if tc else None)
+        if not tc:
+            ops.raw_colsum(dl, self.g(sp["lm"][1]), accumulate=True, M=M, N=V)
         if reducer is not None:
             reducer.bucket_ready()
         gcur = self.buf("g_a", (M, C), torch.float32)
@@ -322,9 +324,10 @@ class Runner:
         mean1, rstd1 = self.buf(tag("mean1"), (M,), torch.float32), self.buf(tag("rstd1"), (M,), torch.float32)
         mean2, rstd2 = self.buf(tag("mean2"), (M,), torch.float32), self.buf(tag("rstd2"), (M,), torch.float32)
         # ---- FFN2: y = h W2^T + b2 (dropout, residual) ----
+        tc = self.mode == "bf16"  # tensor mode: every bias gradient is a by-product of its wgrad GEMM
         self._gemm(gm, h, self.g(L["ffn"][3]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
-                   split_k=self._splits(C, F, M, sm))
-        if li == len(self.spec["layers"]) - 1:  # other layers: fused into the LN1 backward of layer li+1
+                   split_k=self._splits(C, F, M, sm), a_colsum=self.g(L["ffn"][4]) if tc else None)
+        if not tc and li == len(self.spec["layers"]) - 1:  # other layers: fused into the LN1 backward of layer li+1
             ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
         dh = self.buf("dh", (M, F))
         if self._use_relu_mask(F):
@@ -334,17 +337,19 @@ class Runner:
             self._gemm(gm, self.w(L["ffn"][3]), dh, b_major=MAJOR_MN, relu_aux=h)
         # ---- FFN1: h = relu(xn2 W1^T + b1) ----
         self._gemm(dh, xn2, self.g(L["ffn"][1]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
-                   split_k=self._splits(F, C, M, sm))
-        ops.raw_colsum(dh, self.g(L["ffn"][2]), accumulate=True)
+                   split_k=self._splits(F, C, M, sm), a_colsum=self.g(L["ffn"][2]) if tc else None)
+        if not tc:
+            ops.raw_colsum(dh, self.g(L["ffn"][2]), accumulate=True)
         dxn = self.buf("dxn", (M, C))  # activation dtype: bf16 in tensor mode halves this round trip
         self._gemm(dh, self.w(L["ffn"][1]), dxn, b_major=MAJOR_MN)
         # ---- LN2 backward + residual-gradient add + masked copy for the proj GEMMs ----
         g1 = g_other
         ops.raw_ln_bwd(dxn, x1, self.f(L["ln2"][0]), mean2, rstd2, g, g1, self.g(L["ln2"][0]), self.g(L["ln2"][1]),
-                       dxm=gm, dropout=self._drop(L["p"], 4 * li + 1, training), dxm_colsum=self.g(L["proj"][1]))
+                       dxm=gm, dropout=self._drop(L["p"], 4 * li + 1, training),
+                       dxm_colsum=None if tc else self.g(L["proj"][1]))
         # ---- proj: y = att Wp^T + bp (dropout, residual) ----
         self._gemm(gm, att, self.g(L["proj"][0]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
-                   split_k=self._splits(C, D, M, sm))
+                   split_k=self._splits(C, D, M, sm), a_colsum=self.g(L["proj"][1]) if tc else None)
         datt = self.buf("datt", (M, D))
         self._gemm(gm, self.w(L["proj"][0]), datt, b_major=MAJOR_MN)
         # ---- attention ----
@@ -364,7 +369,7 @@ class Runner:
         ops.raw_ln_bwd(dxn, x_in, self.f(L["ln1"][0]), mean1, rstd1, g1, g0, self.g(L["ln1"][0]),
                        self.g(L["ln1"][1]), dxm=gm if nxt is not None else None,
                        dropout=self._drop(nxt["p"], 4 * (li - 1) + 2, training) if nxt is not None else None,
-                       dxm_colsum=self.g(nxt["ffn"][4]) if nxt is not None else None)
+                       dxm_colsum=self.g(nxt["ffn"][4]) if (nxt is not None and not tc) else None)
         return g0
 
     # ------------------------------------------------------------------ #

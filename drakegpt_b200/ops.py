@@ -61,7 +61,7 @@ class Dropout:
 # --------------------------------------------------------------------------- #
 def raw_gemm(A, B, out, *, a_major=MAJOR_K, b_major=MAJOR_K, M=None, N=None, K=None, bias=None, relu=False,
              relu_aux=None, dropout=None, residual=None, out2=None, accumulate=False, split_k=1,
-             relu_mask_out=None, relu_mask_in=None):
+             relu_mask_out=None, relu_mask_in=None, a_colsum=None):
     """out[M,N] = epilogue(A . B^T); see dgpt_gemm in include/drakegpt_b200.h.
 
     relu_mask_out / relu_mask_in: int32 tensors of (N // 32) * M words (tensor mode): the ReLU bit mask the
@@ -93,6 +93,9 @@ def raw_gemm(A, B, out, *, a_major=MAJOR_K, b_major=MAJOR_K, M=None, N=None, K=N
         if mk is not None and (mk.dtype != torch.int32 or mk.numel() < (N // 32) * M or not mk.is_contiguous()):
             raise _lib.KernelError("gemm: relu masks are contiguous int32 tensors of (N // 32) * M words")
     a.relu_mask_out, a.relu_mask_in = _p(relu_mask_out), _p(relu_mask_in)
+    if a_colsum is not None and (a_colsum.dtype != torch.float32 or a_colsum.numel() < M):
+        raise _lib.KernelError("gemm: a_colsum is an fp32 vector of M entries")
+    a.a_colsum = _p(a_colsum)
     if dropout is not None and dropout.p > 0.0:
         a.dropout_p, a.seed, a.site, a.seed_dev = dropout.p, dropout.seed, dropout.site, _p(dropout.seed_dev)
     check(_lib.lib().dgpt_gemm(C.byref(a), _stream()), "dgpt_gemm")

@@ -138,6 +138,10 @@ typedef struct dgpt_gemm_args {
    * (src/model_component.py:321-322: Linear -> ReLU, and its autograd backward). */
   uint32_t* relu_mask_out;
   const uint32_t* relu_mask_in;
+  /* Tensor mode, wgrad form (A and B MN-major, fp32 D): a_colsum[m] += sum_k A[m, k] -- with A = dY^T the bias
+   * gradient of the Linear layer, computed on the tensor core inside the weight-gradient GEMM
+   * (autograd of nn.Linear's bias, src/model_component.py:321-324). */
+  float* a_colsum;
 } dgpt_gemm_args;
 int dgpt_gemm(const dgpt_gemm_args* a, void* stream);
 /* Tensor-mode tiling knob: 1 (default) = one CTA per 128-row tile; 2 = CTA pairs (thread-block cluster of 2,

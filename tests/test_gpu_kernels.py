@@ -153,6 +153,16 @@ def test_gemm_tcgen05_epilogue_and_splitk():
     gacc = torch.ones(96, 136, device=DEV)
     ops.raw_gemm(X.to(DEV), Y.to(DEV), gacc, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True, split_k=8)
     torch.testing.assert_close(gacc.cpu(), 1 + X.float().t() @ Y.float(), rtol=1e-3, atol=5e-2)
+    # ... with the bias gradient (column sums of the stored A = dY) riding on the same GEMM
+    for (Mw, Nw, sk) in [(96, 136, 8), (1536, 384, 4), (80, 384, 2)]:
+        X, Y = torch.randn(Kw, Mw, generator=g).bfloat16(), torch.randn(Kw, Nw, generator=g).bfloat16()
+        if Mw % 8:
+            continue
+        gacc = torch.ones(Mw, Nw, device=DEV)
+        cs = torch.full((Mw,), 2.0, device=DEV)
+        ops.raw_gemm(X.to(DEV), Y.to(DEV), gacc, a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True, split_k=sk, a_colsum=cs)
+        torch.testing.assert_close(gacc.cpu(), 1 + X.float().t() @ Y.float(), rtol=1e-3, atol=5e-2)
+        torch.testing.assert_close(cs.cpu(), 2 + X.float().sum(0), rtol=1e-3, atol=5e-2)
 
 
 @pytest.mark.parametrize("M", [256, 200, 16384 + 96])
