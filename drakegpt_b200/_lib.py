@@ -16,7 +16,7 @@ MAJOR_K, MAJOR_MN = 0, 1
 EXPORTS = [
     "dgpt_last_error", "dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count",
     "dgpt_dropout_keep_host", "dgpt_gemm_set_cta_group", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
-    "dgpt_embed_bwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
+    "dgpt_embed_bwd", "dgpt_embed_ln_fwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
     "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
 ]
 
@@ -75,6 +75,7 @@ def _declare(lib):
         "dgpt_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dgpt_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dgpt_ln_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, f32, vp],
+        "dgpt_embed_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, f32, vp],
         "dgpt_ln_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, f32, u64, vp, u32, i32, i32, vp],
         "dgpt_gemm": [C.POINTER(GemmArgs), vp],
         "dgpt_colsum": [vp, i32, i32, i32, i32, vp, i32, vp],

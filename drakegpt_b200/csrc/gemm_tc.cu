@@ -39,7 +39,8 @@ struct TcParams {
   int vec_ok;      // epilogue operands (bias / residual) allow the vector fast path
   int store_mode;  // StoreMode for D
   int cta_group;   // 1, or 2 = CTA pairs (cluster of 2) sharing each MMA
-  int debug;       // DGPT_GEMM_DEBUG: 1 = epilogue skipped, 2 = no TMA loads / MMAs (timing experiments only)
+  int debug;       // DGPT_GEMM_DEBUG bits (timing experiments only): 1 = epilogue skipped, 2 = no TMA loads / MMAs,
+                   // 4 = epilogue without the output stores, 8 = epilogue without the math
   uint32_t* mask_out;        // ReLU bit mask written by the forward GEMM  [(n / 32) * M + m]
   const uint32_t* mask_in;   // ... and applied by the dgrad GEMM
   float* a_colsum;           // out[m] += sum_k A[m, k]  (bias gradient riding on the wgrad GEMM, CS instantiations)
@@ -462,7 +463,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         const bool fast = kFast && p.vec_ok && mode != kStoreDirect && n + cpb <= p.N;
-        if (fast) {
+        if (p.debug & 8) {
+        } else if (fast) {
           uint32_t mo = 0;
           epi_math32<kFast ? EPI : 0>(ep, m, n, r0, bias_t + half * kCols + b * cpb, tile + lane * 128, row7,
                                       (kFast && (EPI & kEpiMaskIn)) ? mk_in[(b * cpb) >> 5] : 0u, mo);
@@ -502,7 +504,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n, mrow0);
+          if (p.debug & 4) {
+          } else if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n, mrow0);
           else tma_store_2d(&map_d, tile, n, mrow0);
           bulk_commit();
         }

@@ -165,9 +165,17 @@ class Runner:
             if sp["ctx"] is not None and T > sp["ctx"]:
                 raise KernelError(f"sequence length {T} exceeds context_length {sp['ctx']}")
             x = self.buf("x0", (M, C), torch.float32)
-            ops.raw_embed_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C))
+            L0 = sp["layers"][0] if sp["layers"] else None
+            fused0 = L0 is not None and L0["ln1"] is not None  # embedding lookup fused with blocks.0.ln1
+            if fused0:
+                tag = "L0." if save else "tmp."
+                a0 = self.buf(tag + "xn1", (M, C))
+                ops.raw_embed_ln_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C), self.f(L0["ln1"][0]), self.f(L0["ln1"][1]),
+                                     a0, self.buf(tag + "mean1", (M,), torch.float32), self.buf(tag + "rstd1", (M,), torch.float32))
+            else:
+                ops.raw_embed_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C))
             for li, L in enumerate(sp["layers"]):
-                x = self._layer_fwd(li, L, x, B, T, training, save)
+                x = self._layer_fwd(li, L, x, B, T, training, save, ln1_done=(fused0 and li == 0))
             xin = x
             if xin.dtype != self.at:
                 xin = ops.raw_dropout_scale(x, self.buf("x_last_at", x.shape))
@@ -186,7 +194,7 @@ class Runner:
             loss = loss.view(())
         return logits, loss
 
-    def _layer_fwd(self, li, L, x, B, T, training, save):
+    def _layer_fwd(self, li, L, x, B, T, training, save, ln1_done=False):
         M, C = x.shape
         NH, H = L["NH"], L["H"]
         D = NH * H
@@ -197,7 +205,8 @@ class Runner:
         if L["ln1"] is not None:
             a = self.buf(tag("xn1"), (M, C))
             mean1, rstd1 = self.buf(tag("mean1"), (M,), torch.float32), self.buf(tag("rstd1"), (M,), torch.float32)
-            ops.raw_ln_fwd(x, self.f(L["ln1"][0]), self.f(L["ln1"][1]), a, mean1, rstd1)
+            if not ln1_done:
+                ops.raw_ln_fwd(x, self.f(L["ln1"][0]), self.f(L["ln1"][1]), a, mean1, rstd1)
         elif x.dtype != self.at:
             a = ops.raw_dropout_scale(x, self.buf(tag("xn1"), (M, C)))
         else:

@@ -166,6 +166,17 @@ def raw_ln_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     return y
 
 
+def raw_embed_ln_fwd(idx, tok, pos, x, gamma, beta, y, mean, rstd, pos_offset=0, eps=1e-5):
+    """x = tok[idx] + pos (written) and y = LayerNorm(x) in one pass; see dgpt_embed_ln_fwd."""
+    _need_cuda(idx, tok, x, y)
+    B, T = idx.shape
+    V, Cdim = tok.shape
+    check(_lib.lib().dgpt_embed_ln_fwd(_p(idx), _p(tok), _p(pos), _p(x), _p(gamma), _p(beta), _p(y), _DT[y.dtype],
+                                       _p(mean), _p(rstd), B, T, Cdim, V, pos_offset, float(eps), _stream()),
+          "dgpt_embed_ln_fwd")
+    return y
+
+
 def raw_ln_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxm=None, dropout=None, dxm_colsum=None):
     M, Cdim = x.shape
     p, seed, site, sd = 0.0, 0, 0, None

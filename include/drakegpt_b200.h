@@ -92,6 +92,12 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
  * ------------------------------------------------------------------------- */
 int dgpt_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                 float* mean, float* rstd, int M, int C, float eps, void* stream);
+/* Embedding lookup fused with the first block's LayerNorm: x[b,t,:] = tok[idx[b,t]] + pos[t + pos_offset]
+ * (src/model.py:595-597) is written to x AND normalised into y in the same pass (ln1 of blocks.0,
+ * src/model_component.py:505). */
+int dgpt_embed_ln_fwd(const int64_t* idx, const float* tok, const float* pos, float* x, const float* gamma,
+                      const float* beta, void* y, int y_dtype, float* mean, float* rstd, int B, int T, int C,
+                      int V, int pos_offset, float eps, void* stream);
 int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
                 void* dxm, int dxm_dtype, float* dxm_colsum, float p, uint64_t seed,

@@ -46,13 +46,16 @@ def _worker(rank, world, port, out_dir):
         red.finish()
         want = torch.arange(n_live, dtype=torch.float32) * sum(range(1, world + 1))
         assert torch.equal(grad, want), (rank, step)
-    red.bucket_ready()
+    torch.save(grad, os.path.join(out_dir, f"rank{rank}.pt"))
+    red.bucket_ready()  # (leaves one asynchronous bucket in flight: drained below before the group goes away)
     try:
         red.finish()
         raise AssertionError("finish() must refuse a partial reduction")
     except RuntimeError:
         pass
-    torch.save(grad, os.path.join(out_dir, f"rank{rank}.pt"))
+    for w in red._pending:
+        w.wait()
+    dist.barrier()
     dist.destroy_process_group()
 
 
