@@ -3,10 +3,11 @@
 // Forward  (one CTA per (batch, head, 128-query tile), two CTAs resident per SM):
 //   TMA loads Q, K, V tiles (128B swizzle) -> tcgen05.mma S = Q K^T into TMEM (the whole
 //   128 x T score row block fits: no online rescaling) -> 128 softmax threads, one per
-//   query row, read S with tcgen05.ld, apply the causal mask, exp2, Philox dropout, and
-//   write bf16 P straight into the swizzled K-major shared-memory layout the next MMA
-//   reads -> tcgen05.mma O = P V (V consumed MN-major from its row-major tile) -> the same
-//   threads scale by 1/rowsum and store bf16 O at column h*64 (the head concat is free).
+//   query row, read S with tcgen05.ld, apply the causal mask, exp2, counter-based dropout, and
+//   write bf16 P back into TMEM (tcgen05.st, over the S columns already consumed) ->
+//   tcgen05.mma O = P V with P as the TMEM A operand and V consumed MN-major from its
+//   row-major shared-memory tile -> the same threads scale by 1/rowsum and store bf16 O at
+//   column h*64 (the head concat is free).
 //   The T x T probabilities never touch HBM; only the log-sum-exp per row is saved.
 //
 // Backward (one CTA per (batch, head)): recomputes S = Q K^T and dP = dO V^T per
@@ -64,23 +65,29 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile_base, int row, i
 // ===========================================================================
 // forward
 // ===========================================================================
+#ifdef DGPT_ATTN_TS
+__device__ long long g_attn_ts[64];
+#define ATS(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == (gridDim.z / 2) && lane == 0) g_attn_ts[i] = clock64(); } while (0)
+#else
+#define ATS(i) do { } while (0)
+#endif
 static constexpr int kFwdThreads = 192;
-static constexpr int kFwdSmem = 64 * 1024 + 32 * 1024 + 1024 + 128;
+static constexpr int kFwdSmem = 48 * 1024 + 32 * 1024 + 1024 + 128;  // Q, K (two tiles), V; P lives in TMEM
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, AttnTcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                 // 16 KB        | P k-blocks 0..3 (4 x 16 KB) overlay Q and K
-  uint8_t* sK = smem + 16384;         // 2 x 16 KB    | once S has been computed
-  uint8_t* sP = smem;
-  uint8_t* sV = smem + 65536;         // 4 x 8 KB (64 kv rows each)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint8_t* sQ = smem;                 // 16 KB
+  uint8_t* sK = smem + 16384;         // 2 x 16 KB
+  uint8_t* sV = smem + 49152;         // 4 x 8 KB (64 kv rows each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
   uint64_t *qk_full = bars, *v_full = bars + 1, *s_full = bars + 2, *p_full = bars + 3, *o_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 2) ATS(0);
   const int ntile = p.T / QT;
   const int qt = ntile - 1 - (int)blockIdx.x;  // heavier tiles first
   const int h = blockIdx.y, b = blockIdx.z;
@@ -103,6 +110,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp == 2) ATS(1);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -118,6 +126,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
     mbar_wait(qk_full, 0);
+    ATS(8);
     tc_fence_after();
     const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
@@ -133,13 +142,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_wait(v_full, 0);
     mbar_wait(p_full, 0);
     tc_fence_after();
-    const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    // O = P V with P read from TMEM (bf16 pairs, 8 columns per UMMA_K step; it overlays the consumed S columns)
+    // and V from shared memory (MN-major); O accumulates in the columns right above P
     const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
     if (elect_one()) {
       for (int kb = 0; kb < 2 * nkv; ++kb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem, dp0 + (uint64_t)(kb * 1024 + k * 2), dv0 + (uint64_t)(kb * 512 + k * 128), idesc_o, (kb | k) > 0);
+          tc_mma_bf16_ts(tmem + nkv * 64, tmem + kb * 32 + k * 8, dv0 + (uint64_t)(kb * 512 + k * 128), idesc_o, (kb | k) > 0);
       }
       tc_commit(o_full);
     }
@@ -154,6 +164,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t seed = p.seed;
     if (p.thr && p.seed_dev) seed += *p.seed_dev;
     mbar_wait(s_full, 0);
+    if (warp == 2) ATS(2);
     tc_fence_after();
     // tcgen05.ld is warp-collective: loop bounds must be warp-uniform, so use the LAST row of this
     // warp to decide which 32-column chunks are fully masked
@@ -167,6 +178,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int j = 0; j < 32; ++j)
         if (c + j <= qg) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
+    if (warp == 2) ATS(3);
     const float sc = p.scale * kLog2e;
     const float msc = mx * sc;
     float sum = 0.f;
@@ -193,22 +205,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             if (dropout_word(g, j) < p.thr) e[j] = 0.f;
         }
       }
-      store_row32_sw128(sP, row, c, e);
+      // bf16 P, two keys per 32-bit TMEM column, written over S columns [c / 2, c / 2 + 16): this thread has
+      // already consumed them (chunks <= c of its own row)
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(e[2 * j], e[2 * j + 1]);
+      tmem_st16(taddr + (c >> 1), pk);
     }
     if (p.lse) p.lse[((int64_t)b * p.NH + h) * p.T + qg] = mx * p.scale + logf(sum);
-    fence_proxy_async();
+    tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full);
+    if (warp == 2) ATS(4);
     // epilogue
     mbar_wait(o_full, 0);
+    if (warp == 2) ATS(5);
     tc_fence_after();
     const float oscale = p.inv_keep / sum;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.o) + (int64_t)(row0 + qg) * p.o_rs + h * HD;
 #pragma unroll
     for (int c = 0; c < HD; c += 32) {
       uint32_t r[32];
-      tmem_ld32(taddr + c, r);
+      tmem_ld32(taddr + nkv * 64 + c, r);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -221,12 +240,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   }
+  if (warp == 2) ATS(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<256>(tmem);
   }
+  if (warp == 2) ATS(7);
 }
 
 // ===========================================================================
@@ -282,10 +303,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   float* lse_s = reinterpret_cast<float*>(sSt + 16384);  // [256]  lse * log2(e)
   float* D_s = lse_s + 256;                              // [256]  rowsum(dO * O)
   uint64_t* bars = reinterpret_cast<uint64_t*>(D_s + 256);
-  uint64_t *ld_full = bars, *st_full = bars + 1, *ps_full = bars + 2, *drained = bars + 3, *acc_done = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t *ld_a = bars, *st_full = bars + 1, *ps_full = bars + 2, *drained = bars + 3, *acc_done = bars + 4;
+  uint64_t *ld_b = bars + 5, *ld_c = bars + 6;  // loads arrive in three stages so that pair (0,0) starts after half of them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef DGPT_ATTN_TS
+#define BTS(i) do { if (blockIdx.x == 0 && blockIdx.y == (gridDim.y / 2) && warp == 2 && lane == 0) g_attn_ts[i] = clock64(); } while (0)
+#else
+#define BTS(i) do { } while (0)
+#endif
+  BTS(0);
   const int h = blockIdx.x, b = blockIdx.y;
   const int ntile = p.T / QT;
   const int npair = ntile == 1 ? 1 : 3;  // (0,0) | (0,0),(1,0),(1,1)
@@ -297,7 +325,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&map_do);
     prefetch_tensormap(&map_o);
-    mbar_init(ld_full, 1);
+    mbar_init(ld_a, 1);
+    mbar_init(ld_b, 1);
+    mbar_init(ld_c, 1);
     mbar_init(st_full, 1);
     mbar_init(ps_full, 8);
     mbar_init(drained, 8);
@@ -313,13 +343,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(ld_full, 16384 * 5 * ntile);
-      for (int t = 0; t < ntile; ++t) {
-        tma_load_2d(sG + t * 16384, &map_do, ld_full, h * HD, row0 + t * QT);
-        tma_load_2d(sPd + t * 16384, &map_o, ld_full, h * HD, row0 + t * QT);  // O: only for D = rowsum(dO * O)
-        tma_load_2d(sQ + t * 16384, &map_q, ld_full, h * HD, row0 + t * QT);
-        tma_load_2d(sK + t * 16384, &map_k, ld_full, h * HD, row0 + t * QT);
-        tma_load_2d(sV + t * 16384, &map_v, ld_full, h * HD, row0 + t * QT);
+      // stage A: everything pair (0,0) needs; B: query tile 1 (pairs (1,0), (1,1)); C: key tile 1 (pair (1,1)).
+      // O is only needed for D = rowsum(dO * O): O_0 lands in the Pd tile, O_1 in the store staging tile
+      // (both are consumed before their first other use).
+      mbar_expect_tx(ld_a, 16384 * 5);
+      tma_load_2d(sG, &map_do, ld_a, h * HD, row0);
+      tma_load_2d(sPd, &map_o, ld_a, h * HD, row0);
+      tma_load_2d(sQ, &map_q, ld_a, h * HD, row0);
+      tma_load_2d(sK, &map_k, ld_a, h * HD, row0);
+      tma_load_2d(sV, &map_v, ld_a, h * HD, row0);
+      if (ntile > 1) {
+        mbar_expect_tx(ld_b, 16384 * 3);
+        tma_load_2d(sG + 16384, &map_do, ld_b, h * HD, row0 + QT);
+        tma_load_2d(sSt, &map_o, ld_b, h * HD, row0 + QT);
+        tma_load_2d(sQ + 16384, &map_q, ld_b, h * HD, row0 + QT);
+        mbar_expect_tx(ld_c, 16384 * 2);
+        tma_load_2d(sK + 16384, &map_k, ld_c, h * HD, row0 + QT);
+        tma_load_2d(sV + 16384, &map_v, ld_c, h * HD, row0 + QT);
       }
     }
   } else if (warp == 1) {
@@ -327,7 +367,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP
     constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, 0, 1);  // dQ
     constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, 1, 1); // dV, dK
-    mbar_wait(ld_full, 0);
+    mbar_wait(ld_a, 0);
     tc_fence_after();
     // descriptor bases; the start-address field counts 16-byte units (a 16 KB tile = 1024, 2 KB = 128, 32 B = 2)
     const uint64_t kQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), kK = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
@@ -339,6 +379,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int pr = 0; pr < npair; ++pr) {
       const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
       const uint32_t ph = pr & 1;
+      if (pr == 1) mbar_wait(ld_b, 0);
+      if (pr == 2) mbar_wait(ld_c, 0);
+      if (pr > 0) tc_fence_after();
       // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal
       // test and the dropout quads (which run along the key axis) are per-thread like in forward
       if (elect_one()) {
@@ -384,30 +427,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint64_t seed = p.seed;
     if (DROP && p.seed_dev) seed += *p.seed_dev;
-    // D_i = dO_i . O_i for every query row, read back from the TMA-loaded (swizzled) tiles
-    mbar_wait(ld_full, 0);
-    if (ct < p.T) {
-      const int tl = ct >> 7, r = ct & 127;
-      const uint8_t* gr = sG + tl * 16384 + r * 128;
-      const uint8_t* orow = sPd + tl * 16384 + r * 128;
-      float acc = 0.f;
+    // D_i = dO_i . O_i for every query row of tile tl, read back from the TMA-loaded (swizzled) tiles
+    auto compute_D = [&](int tl, const uint8_t* o_tile) {
+      if (ct < QT) {
+        const int r = ct;
+        const uint8_t* gr = sG + tl * 16384 + r * 128;
+        const uint8_t* orow = o_tile + r * 128;
+        float acc = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int off = (c ^ (r & 7)) << 4;
-        const uint4 g = *reinterpret_cast<const uint4*>(gr + off), o = *reinterpret_cast<const uint4*>(orow + off);
-        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+        for (int c = 0; c < 8; ++c) {
+          const int off = (c ^ (r & 7)) << 4;
+          const uint4 g = *reinterpret_cast<const uint4*>(gr + off), o = *reinterpret_cast<const uint4*>(orow + off);
+          const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[t]));
-          const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
-          acc = fmaf(gf.x, of.x, acc);
-          acc = fmaf(gf.y, of.y, acc);
+          for (int t = 0; t < 4; ++t) {
+            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[t]));
+            const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
+            acc = fmaf(gf.x, of.x, acc);
+            acc = fmaf(gf.y, of.y, acc);
+          }
         }
+        D_s[tl * QT + r] = acc;
+        lse_s[tl * QT + r] = p.lse[((int64_t)b * p.NH + h) * p.T + tl * QT + r] * kLog2e;
       }
-      D_s[ct] = acc;
-      lse_s[ct] = p.lse[((int64_t)b * p.NH + h) * p.T + ct] * kLog2e;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // D/lse visible; the O tiles may now be overwritten by Pd
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // D/lse visible; the O tile may now be overwritten
+    };
+    BTS(1);
+    mbar_wait(ld_a, 0);
+    BTS(2);
+    compute_D(0, sPd);
     const float sc = p.scale * kLog2e;
     int n_stores = 0;
 
@@ -439,11 +487,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       ++n_stores;
     };
 
+    BTS(3);
     for (int pr = 0; pr < npair; ++pr) {
       const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+      BTS(4 + 4 * pr);
       mbar_wait(st_full, pr & 1);  // also implies the accumulate MMAs of the previous pair retired
+      BTS(5 + 4 * pr);
       tc_fence_after();
       if (pr == 1) {               // (0,0) finished query tile 0
+        mbar_wait(ld_b, 0);
+        compute_D(1, sSt);         // before the first drain reuses the staging tile
         drain(TM_DQ, &map_dq, 0);
       } else if (pr == 2) {        // (1,0) finished key tile 0
         drain(TM_DV, &map_dv, 0);
@@ -454,6 +507,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(drained);
       }
+      BTS(6 + 4 * pr);
       const int qi = i * QT + rowl;  // this thread's query row
       const float lse2 = lse_s[qi], Dq = D_s[qi];
       const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + (uint64_t)(j * QT);
@@ -470,14 +524,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ps_full);
+      BTS(7 + 4 * pr);
     }
+    BTS(16);
     mbar_wait(acc_done, 0);
+    BTS(17);
     tc_fence_after();
     const int last = ntile - 1;
     drain(TM_DV, &map_dv, last);
     drain(TM_DK, &map_dk, last);
     drain(TM_DQ, &map_dq, last);
     if (ct == 0) bulk_wait<0>();
+    BTS(18);
   }
   tc_fence_before();
   __syncthreads();
@@ -534,6 +592,16 @@ int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
   AttnTcP p = make_tc_params(a);
   dim3 grid(a->Tk / QT, a->NH, a->B);
   attn_fwd_tc_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, p);
+#ifdef DGPT_ATTN_TS
+  {
+    cudaStreamSynchronize(st);
+    long long h[64];
+    cudaMemcpyFromSymbol(h, g_attn_ts, sizeof(h));
+    printf("attn fwd CTA(qt=1,h=0,b=B/2): setup %lld | qk load done %lld | S ready %lld | pass1 %lld | pass2 %lld | PV wait %lld | epilogue %lld | exit %lld\n",
+           h[1] - h[0], h[8] - h[0], h[2] - h[0], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+    fflush(stdout);
+  }
+#endif
   return check_launch("attn_fwd_tc");
 }
 
@@ -561,6 +629,19 @@ int launch_attn_bwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
   dim3 grid(a->NH, a->B);
   if (p.thr) attn_bwd_tc_kernel<true><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
   else attn_bwd_tc_kernel<false><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
+#ifdef DGPT_ATTN_TS
+  {
+    cudaStreamSynchronize(st);
+    long long h[64];
+    cudaMemcpyFromSymbol(h, g_attn_ts, sizeof(h));
+    printf("attn bwd CTA: setup %lld | load wait %lld | D %lld |", h[1] - h[0], h[2] - h[1], h[3] - h[2]);
+    for (int pr = 0; pr < 3; ++pr)
+      printf(" pair%d: S/dP wait %lld, drains %lld, chunks %lld |", pr, h[5 + 4 * pr] - h[4 + 4 * pr], h[6 + 4 * pr] - h[5 + 4 * pr],
+             h[7 + 4 * pr] - h[6 + 4 * pr]);
+    printf(" acc wait %lld | final drains %lld | total %lld\n", h[17] - h[16], h[18] - h[17], h[18] - h[0]);
+    fflush(stdout);
+  }
+#endif
   return check_launch("attn_bwd_tc");
 }
 
