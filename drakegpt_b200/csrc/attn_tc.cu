@@ -169,14 +169,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // tcgen05.ld is warp-collective: loop bounds must be warp-uniform, so use the LAST row of this
     // warp to decide which 32-column chunks are fully masked
     const int qg_max = qt * QT + quad * 32 + 31;
+    // chunks entirely left of the diagonal for every row of this warp need no per-element causal test
+    const int qg_min = qt * QT + quad * 32;
     float mx = -INFINITY;
     for (int c = 0; c < ncols && c <= qg_max; c += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + c, r);
       tmem_ld_wait();
+      if (c + 31 <= qg_min) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c + j <= qg) mx = fmaxf(mx, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j <= qg) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
     }
     if (warp == 2) ATS(3);
     const float sc = p.scale * kLog2e;
@@ -192,11 +199,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
+        if (c + 31 <= qg_min) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = (c + j <= qg) ? exp2f(__uint_as_float(r[j]) * sc - msc) : 0.f;
-          sum += v;
-          e[j] = v;
+          for (int j = 0; j < 32; ++j) {
+            const float v = exp2f(__uint_as_float(r[j]) * sc - msc);
+            sum += v;
+            e[j] = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = (c + j <= qg) ? exp2f(__uint_as_float(r[j]) * sc - msc) : 0.f;
+            sum += v;
+            e[j] = v;
+          }
         }
         if (p.thr) {  // the 32 keys of this chunk are one mask group (T % 32 == 0)
           const DropGroup g = dropout_group(seed, p.site, (base + c) >> 5);
