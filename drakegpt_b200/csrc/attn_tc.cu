@@ -274,14 +274,13 @@ static constexpr int kBwdSmem = 8 * 16384 + 2 * 32768 + 16384 + 2048 + 1024 + 12
 
 // one 32-key chunk of one query row: P, dropout, dS -> swizzled bf16 rows of the Pd / dS tiles
 template <bool DIAG, bool DROP>
-__device__ __forceinline__ void bwd_chunk(const AttnTcP& p, uint32_t lane_addr_st, uint32_t lane_addr_dp, uint8_t* sPd,
-                                          uint8_t* sDs, int row, int k0, float sc, float lse2, float Dq, uint64_t seed,
-                                          uint64_t base) {
+__device__ __forceinline__ void bwd_chunk_math(const AttnTcP& p, uint32_t lane_addr_st, uint32_t lane_addr_dp, int row, int k0,
+                                               float sc, float lse2, float Dq, uint64_t seed, uint64_t base,
+                                               float (&pd)[32], float (&ds)[32]) {
   uint32_t st[32], dp[32];
   tmem_ld32(lane_addr_st + k0, st);
   tmem_ld32(lane_addr_dp + k0, dp);
   tmem_ld_wait();
-  float pd[32], ds[32];
   DropGroup g = {0u, 0u};
   if (DROP) g = dropout_group(seed, p.site, (base + k0) >> 5);  // the chunk's 32 keys are one mask group
 #pragma unroll
@@ -298,8 +297,6 @@ __device__ __forceinline__ void bwd_chunk(const AttnTcP& p, uint32_t lane_addr_s
     pd[t] = pdv;
     ds[t] = pv * (dpv - Dq) * p.scale;
   }
-  store_row32_sw128(sPd, row, k0, pd);
-  store_row32_sw128(sDs, row, k0, ds);
 }
 
 template <bool DROP>
@@ -321,7 +318,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(D_s + 256);
   uint64_t *ld_a = bars, *st_full = bars + 1, *ps_full = bars + 2, *drained = bars + 3, *acc_done = bars + 4;
   uint64_t *ld_b = bars + 5, *ld_c = bars + 6;  // loads arrive in three stages so that pair (0,0) starts after half of them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* acc_free = bars + 7;                // the accumulate MMAs of a pair have retired (Pd / dS tiles reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef DGPT_ATTN_TS
@@ -348,16 +346,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(ps_full, 8);
     mbar_init(drained, 8);
     mbar_init(acc_done, 1);
+    mbar_init(acc_free, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
-
-  if (warp == 0) {
+  if (warp == 0) {  // the loads do not depend on TMEM: issue them before the allocation and the CTA-wide barrier
+    __syncwarp();
     if (elect_one()) {
       // stage A: everything pair (0,0) needs; B: query tile 1 (pairs (1,0), (1,1)); C: key tile 1 (pair (1,1)).
       // O is only needed for D = rowsum(dO * O): O_0 lands in the Pd tile, O_1 in the store staging tile
@@ -378,6 +371,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tma_load_2d(sV + 16384, &map_v, ld_c, h * HD, row0 + QT);
       }
     }
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+  if (warp == 0) {
+    // (loads were issued before the TMEM allocation, see above)
   } else if (warp == 1) {
     // whole warp in uniform control flow, one elected lane issues (see forward)
     constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP
@@ -392,14 +395,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint64_t mQ = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024), mK = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);
     const uint64_t mG = make_smem_desc_sw128(smem_u32(sG), 8192, 1024);
     const uint64_t mPd = make_smem_desc_sw128(smem_u32(sPd), 16384, 1024), mDs = make_smem_desc_sw128(smem_u32(sDs), 16384, 1024);
-    for (int pr = 0; pr < npair; ++pr) {
+    // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal test and the dropout
+    // groups (which run along the key axis) are per-thread like in forward
+    auto issue_s_dp = [&](int pr) {
       const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
-      const uint32_t ph = pr & 1;
-      if (pr == 1) mbar_wait(ld_b, 0);
-      if (pr == 2) mbar_wait(ld_c, 0);
-      if (pr > 0) tc_fence_after();
-      // S = Q_i K_j^T and dP = dO_i V_j^T: rows = queries, so the softmax statistics, the causal
-      // test and the dropout quads (which run along the key axis) are per-thread like in forward
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -410,7 +409,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_commit(st_full);
       }
       __syncwarp();
-      mbar_wait(ps_full, ph);
+    };
+    issue_s_dp(0);
+    for (int pr = 0; pr < npair; ++pr) {
+      const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+      mbar_wait(ps_full, pr & 1);  // Pd / dS of this pair are in shared memory; S / dP have been consumed
+      // S / dP of the NEXT pair go first: the compute threads turn them into Pd / dS while the accumulate MMAs
+      // below still run (they hold their results in registers until acc_free says the tiles may be rewritten)
+      if (pr + 1 < npair) {
+        mbar_wait(pr + 1 == 1 ? ld_b : ld_c, 0);
+        tc_fence_after();
+        issue_s_dp(pr + 1);
+      }
       if (pr > 0) mbar_wait(drained, (pr - 1) & 1);
       tc_fence_after();
       const uint32_t acc_vk = (pr == 1) ? 1u : 0u;  // second pair of key tile 0 accumulates
@@ -429,6 +439,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int k = 0; k < 8; ++k)
           tc_mma_bf16(tmem + TM_DQ, kDs + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), mK + (uint64_t)(j * 1024 + k * 128), id_kmn,
                       acc_q | (k > 0));
+        tc_commit(acc_free);
         if (pr == npair - 1) tc_commit(acc_done);
       }
       __syncwarp();
@@ -443,6 +454,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint64_t seed = p.seed;
     if (DROP && p.seed_dev) seed += *p.seed_dev;
+    // log-sum-exp of every query row, fetched while the tiles are still in flight (one row per thread)
+    if (ct < p.T) lse_s[ct] = p.lse[((int64_t)b * p.NH + h) * p.T + ct] * kLog2e;
     // D_i = dO_i . O_i for every query row of tile tl, read back from the TMA-loaded (swizzled) tiles
     auto compute_D = [&](int tl, const uint8_t* o_tile) {
       if (ct < QT) {
@@ -464,7 +477,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
         }
         D_s[tl * QT + r] = acc;
-        lse_s[tl * QT + r] = p.lse[((int64_t)b * p.NH + h) * p.T + tl * QT + r] * kLog2e;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // D/lse visible; the O tile may now be overwritten
     };
@@ -506,36 +518,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     BTS(3);
     for (int pr = 0; pr < npair; ++pr) {
       const int i = pr == 0 ? 0 : 1, j = pr == 2 ? 1 : 0;
+      if (pr == 1) {               // D of query tile 1 (its O tile sits in the staging tile until the first drain)
+        mbar_wait(ld_b, 0);
+        compute_D(1, sSt);
+      }
       BTS(4 + 4 * pr);
-      mbar_wait(st_full, pr & 1);  // also implies the accumulate MMAs of the previous pair retired
+      mbar_wait(st_full, pr & 1);
       BTS(5 + 4 * pr);
       tc_fence_after();
-      if (pr == 1) {               // (0,0) finished query tile 0
-        mbar_wait(ld_b, 0);
-        compute_D(1, sSt);         // before the first drain reuses the staging tile
-        drain(TM_DQ, &map_dq, 0);
-      } else if (pr == 2) {        // (1,0) finished key tile 0
-        drain(TM_DV, &map_dv, 0);
-        drain(TM_DK, &map_dk, 0);
-      }
+      const int qi = i * QT + rowl;  // this thread's query row
+      const float lse2 = lse_s[qi], Dq = D_s[qi];
+      const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + (uint64_t)(j * QT);
+      float pd[32], ds[32];
+      // first chunk: math into registers -- the accumulate MMAs of the previous pair may still be reading Pd / dS
+      if (i == j) bwd_chunk_math<true, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, rowl, half * 64, sc, lse2, Dq, seed, base, pd, ds);
+      else bwd_chunk_math<false, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, rowl, half * 64, sc, lse2, Dq, seed, base, pd, ds);
       if (pr > 0) {
+        mbar_wait(acc_free, (pr - 1) & 1);  // previous pair's accumulators final, its Pd / dS tiles free
+        tc_fence_after();
+        if (pr == 1) {             // (0,0) finished query tile 0
+          drain(TM_DQ, &map_dq, 0);
+        } else {                   // (1,0) finished key tile 0
+          drain(TM_DV, &map_dv, 0);
+          drain(TM_DK, &map_dk, 0);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(drained);
       }
       BTS(6 + 4 * pr);
-      const int qi = i * QT + rowl;  // this thread's query row
-      const float lse2 = lse_s[qi], Dq = D_s[qi];
-      const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qi) * (uint64_t)p.T + (uint64_t)(j * QT);
-      if (i == j) {
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32)
-          bwd_chunk<true, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, sPd, sDs, rowl, half * 64 + c, sc, lse2, Dq, seed, base);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32)
-          bwd_chunk<false, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, sPd, sDs, rowl, half * 64 + c, sc, lse2, Dq, seed, base);
-      }
+      store_row32_sw128(sPd, rowl, half * 64, pd);
+      store_row32_sw128(sDs, rowl, half * 64, ds);
+      if (i == j) bwd_chunk_math<true, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, rowl, half * 64 + 32, sc, lse2, Dq, seed, base, pd, ds);
+      else bwd_chunk_math<false, DROP>(p, lane_addr + TM_ST, lane_addr + TM_DP, rowl, half * 64 + 32, sc, lse2, Dq, seed, base, pd, ds);
+      store_row32_sw128(sPd, rowl, half * 64 + 32, pd);
+      store_row32_sw128(sDs, rowl, half * 64 + 32, ds);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -547,9 +564,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     BTS(17);
     tc_fence_after();
     const int last = ntile - 1;
-    drain(TM_DV, &map_dv, last);
-    drain(TM_DK, &map_dk, last);
-    drain(TM_DQ, &map_dq, last);
+    {
+      // the last three accumulators leave together: dV -> the Pd tile, dK -> the dS tile (no MMA reads them any
+      // more), dQ -> the staging tile; one fence and one barrier, then three TMA stores
+      if (n_stores > 0) {
+        if (ct == 0) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      uint8_t* tiles[3] = {sPd, sDs, sSt};
+      const uint32_t cols[3] = {TM_DV, TM_DK, TM_DQ};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + cols[q] + half * 32, r);
+        tmem_ld_wait();
+        uint8_t* rp = tiles[q] + rowl * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+          w.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          w.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          w.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          *reinterpret_cast<uint4*>(rp + (((half * 4 + j) ^ (rowl & 7)) << 4)) = w;
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ct == 0) {
+        tma_store_2d(&map_dv, sPd, h * HD, row0 + last * QT);
+        tma_store_2d(&map_dk, sDs, h * HD, row0 + last * QT);
+        tma_store_2d(&map_dq, sSt, h * HD, row0 + last * QT);
+        bulk_commit();
+      }
+    }
     if (ct == 0) bulk_wait<0>();
     BTS(18);
   }
