@@ -674,6 +674,11 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   // tile N: widest tile that still yields >= ~1 wave of CTAs
   int sms = dgpt_sm_count();
   if (sms <= 0) sms = 148;
+  {  // DGPT_GEMM_SMS: leave some SMs to concurrently running kernels (the NCCL all-reduce of the data-parallel step)
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("DGPT_GEMM_SMS"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && cap < sms) sms = cap;
+  }
   const int m_tiles = ceil_div(a->M, TBM);
   // 128 x 256 tiles ingest 25 % fewer operand bytes per MMA cycle than 128 x 128; a ragged last column
   // tile (N = 1152 -> 4.5 tiles) costs less than that as soon as N >= 1024 (TMA zero-fills, the store clips)

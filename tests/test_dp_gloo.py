@@ -36,16 +36,18 @@ def _worker(rank, world, port, out_dir):
     groups = [("lm_head.",)] + [(f"blocks.{i}.",) for i in (2, 1, 0)] + [("token_embedding_table.", "position_embedding_table.")]
     ranges = bucket_ranges(slots, n_live, groups)
     grad = torch.arange(n_live, dtype=torch.float32) * (rank + 1)  # rank-dependent gradient
-    red = GradAllReducer(grad, ranges)
-    assert red.grad_scale == 1.0 / world
-    for step in range(2):  # reusable across steps
-        if step:
-            grad.copy_(torch.arange(n_live, dtype=torch.float32) * (rank + 1))
-        for _ in ranges:
-            red.bucket_ready()
-        red.finish()
-        want = torch.arange(n_live, dtype=torch.float32) * sum(range(1, world + 1))
-        assert torch.equal(grad, want), (rank, step)
+    want = torch.arange(n_live, dtype=torch.float32) * sum(range(1, world + 1))
+    for overlap in (False, True):  # one message at the end of backward (default) / bucketed and overlapped
+        grad.copy_(torch.arange(n_live, dtype=torch.float32) * (rank + 1))
+        red = GradAllReducer(grad, ranges, overlap=overlap)
+        assert red.grad_scale == 1.0 / world and red.overlap == overlap
+        for step in range(2):  # reusable across steps
+            if step:
+                grad.copy_(torch.arange(n_live, dtype=torch.float32) * (rank + 1))
+            for _ in ranges:
+                red.bucket_ready()
+            red.finish()
+            assert torch.equal(grad, want), (rank, step, overlap)
     torch.save(grad, os.path.join(out_dir, f"rank{rank}.pt"))
     red.bucket_ready()  # (leaves one asynchronous bucket in flight: drained below before the group goes away)
     try:
