@@ -60,14 +60,20 @@ template <int BN, int CG, int RESBUFS, int CS = 0>
 struct TcCfg {
   static constexpr int kBBytes = (BN / CG) * TBK * 2;
   static constexpr int kStageBytes = TBM * TBK * 2 + kBBytes;
-  static constexpr int kStagingBufs = RESBUFS ? RESBUFS : 2;       // 4 KB staging buffers per epilogue warp
+  // 4 KB staging buffers per epilogue warp: 2, or (residual epilogues) the warp's fp32 blocks of one tile
+  // (RESBUFS = 2) or of two tiles (RESBUFS = 4)
+  static constexpr int kResBlocks = BN / 2 / 32;
+  static constexpr int kStagingBufs = RESBUFS ? (RESBUFS / 2) * kResBlocks : 2;
   static constexpr int kStagingBytes = 8 * kStagingBufs * 4096;
   static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
   static constexpr int kBarBytes = 512;
   static constexpr int kRing = kSmemMax - kStagingBytes - kBiasBytes - kBarBytes;
   static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
-  static constexpr int kTmemCols = CS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);  // powers of two; CS: + 2 x 16 column-sum columns
-  static_assert(!CS || 2 * BN + 32 <= 512, "no TMEM room for the column-sum accumulators");
+  // power of two covering both accumulators (+ 2 x 16 column-sum columns with CS)
+  static constexpr int kTmemNeed = 2 * BN + (CS ? 32 : 0);
+  static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "no TMEM room");
+  static_assert(BN != 192 || CG == 1 || true, "192-column tiles are launched single-CTA only");
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
   static_assert(kStages >= 3, "shared-memory ring too shallow");
 };
@@ -385,10 +391,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ew = warp - 2;
     const int quad = warp & 3;   // TMEM lanes [32*quad, 32*quad+32)
     const int half = ew >> 2;    // columns [half*BN/2, (half+1)*BN/2)
-    constexpr int kCols = BN / 2;
     constexpr bool kFast = EPI >= 0;
+    // Column split between the two warps of a quadrant.  128- and 256-column tiles: half each.  192-column tiles
+    // (the N = 384 GEMMs of this model: 2 tiles per row instead of 3, i.e. A is re-read twice instead of three
+    // times and the per-k-block bookkeeping is paid twice instead of three times): 96 fp32 columns each, but bf16
+    // output leaves in 64-column blocks, so there the first warp takes 128 columns and the second 64.
+    constexpr int kCols = BN == 192 ? 128 : BN / 2;  // upper bound of a warp's columns (array sizes)
     constexpr int CPB = (kFast && OBF) ? 64 : 32;  // accumulator columns per staging block (fast path; residual bookkeeping)
-    constexpr int NBLK = kCols / CPB;
+    constexpr int NBLK = (BN / 2) / CPB;            // residual bookkeeping (fp32 output: BN / 2 columns per warp)
     constexpr int kBufs = Cfg::kStagingBufs;
     uint8_t* my_stage = staging + ew * (kBufs * 4096);
     uint64_t* my_res_bar = res_bar + ew * 2;
@@ -401,14 +411,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int mode = p.store_mode;
     const bool out_bf16 = kFast ? (OBF != 0) : (ep.d_dtype == DGPT_BF16);
     const int cpb = out_bf16 ? 64 : 32;  // compile-time on the fast path, run-time in the generic kernel
-    const int nblk = kCols / cpb;
+    const int col_beg = (BN == 192 && out_bf16) ? half * 128 : half * (BN / 2);            // first column of this warp
+    const int ncols = (BN == 192 && out_bf16) ? (half ? 64 : 128) : BN / 2;                // ... and how many
+    const int nblk = ncols / cpb;
     const int row7 = lane & 7;
 
     constexpr bool kResAhead = RESBUFS == 4;  // a second buffer pair: fetch a whole tile ahead
     auto res_prefetch = [&](int t, int par) {  // lane 0: residual blocks of tile t -> buffers [NBLK par, NBLK par + NBLK)
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
-      const int nb = n0 + half * kCols;
+      const int nb = n0 + col_beg;
       int cnt = 0;
       for (int b = 0; b < NBLK; ++b) cnt += (nb + b * CPB < p.N) ? 1 : 0;
       if (cnt == 0 || m0 + quad * 32 >= p.M) { mbar_arrive(&my_res_bar[par]); return; }
@@ -424,13 +436,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       ep.first_split = (ks == 0);
       const int mrow0 = (p.debug & 1) ? p.M : m0 + quad * 32;  // debug bit 0: skip all epilogue work
       const int m = mrow0 + lane;
-      const int nbeg = n0 + half * kCols;
+      const int nbeg = n0 + col_beg;
       const bool active = mrow0 < p.M && nbeg < p.N;
       // stage this tile's bias slice (each warp an eighth) while the accumulator is still being produced
       float* bias_t = bias_s + acc * BN;
       if (kFast && (EPI & kEpiBias)) {
         const int col = ew * (BN / 8) + lane * 4;
-        if (lane * 4 < BN / 8 && n0 + col < p.N)
+        if (lane * 4 < BN / 8 && n0 + col < p.N)  // (BN / 8 = 16, 24 or 32 floats per warp)
           *reinterpret_cast<float4*>(bias_t + col) = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + col));
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       }
@@ -438,13 +450,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (kFast && (EPI & kEpiMaskIn)) {
 #pragma unroll
         for (int w = 0; w < kCols / 32; ++w)
-          mk_in[w] = (active && m < p.M && nbeg + 32 * w < p.N) ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + m) : 0u;
+          mk_in[w] = (active && m < p.M && 32 * w < ncols && nbeg + 32 * w < p.N) ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + m) : 0u;
       }
       const int par = kResAhead ? (it & 1) : 0;
       if (kRes && !(p.debug & 1)) mbar_wait(&my_res_bar[par], (uint32_t)(kResAhead ? (it >> 1) : it) & 1u);
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kCols);
+      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col_beg);
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
         const int n = nbeg + b * cpb;
@@ -466,13 +478,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.debug & 8) {
         } else if (fast) {
           uint32_t mo = 0;
-          epi_math32<kFast ? EPI : 0>(ep, m, n, r0, bias_t + half * kCols + b * cpb, tile + lane * 128, row7,
+          epi_math32<kFast ? EPI : 0>(ep, m, n, r0, bias_t + col_beg + b * cpb, tile + lane * 128, row7,
                                       (kFast && (EPI & kEpiMaskIn)) ? mk_in[(b * cpb) >> 5] : 0u, mo);
           if (kFast && (EPI & kEpiMaskOut)) {
             if (m < p.M) p.mask_out[(size_t)(n >> 5) * p.M + m] = mo;
           }
           if (cpb == 64) {
-            epi_math32<kFast ? EPI : 0>(ep, m, n + 32, r1, bias_t + half * kCols + b * cpb + 32, tile + lane * 128, row7,
+            epi_math32<kFast ? EPI : 0>(ep, m, n + 32, r1, bias_t + col_beg + b * cpb + 32, tile + lane * 128, row7,
                                         (kFast && (EPI & kEpiMaskIn)) ? mk_in[((b * cpb) >> 5) + 1] : 0u, mo);
             if (kFast && (EPI & kEpiMaskOut)) {
               if (m < p.M) p.mask_out[(size_t)((n >> 5) + 1) * p.M + m] = mo;
@@ -659,7 +671,7 @@ struct TcMaps {
 // pair tiles whenever requested and the row-tile count is even, single-CTA tiles otherwise
 template <int BN, int A_MN, int B_MN, int EPI, int OBF, int RESBUFS = 0>
 static int launch_cfg(const TcMaps& m, const TcParams& p, int sms, cudaStream_t st) {
-  if (p.cta_group == 2) {
+  if (p.cta_group == 2 && BN != 192) {
     const int total = (p.m_tiles / 2) * p.n_tiles * p.split_k;
     return launch_one<BN, A_MN, B_MN, EPI, OBF, 2, RESBUFS>(m.a, m.b_half, m.d, m.r, p, 2 * min(total, sms / 2), st);
   }
@@ -685,6 +697,12 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   int BN = 256;
   if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024) || a->a_colsum) BN = 128;
   if (BN == 256 && m_tiles * ceil_div(a->N, 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
+  // 192-column tiles for N = 192, 384, 576, 960 (the model's N = 384 GEMMs): two tiles per row instead of three
+  static int bn192_env = -1;
+  if (bn192_env < 0) { const char* e = getenv("DGPT_GEMM_BN192"); bn192_env = e ? atoi(e) : 1; }
+  // (measured: ~5 % faster for the dgrad / wgrad GEMMs with >= 8 row tiles; slower with the residual epilogue, whose
+  // three staging buffers per warp leave a 3-stage ring, and for small wgrads that would need > 20 K splits)
+  if (bn192_env && BN == 128 && a->N % 192 == 0 && a->N % 256 != 0 && a->N < 1024 && m_tiles >= 8 && !a->residual) BN = 192;
   const int n_tiles = ceil_div(a->N, BN);
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -751,8 +769,8 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (p.store_mode == kStoreDirect || !p.vec_ok || a->D2 || a->relu_aux) epi = -1;
   if (epi > 0 && (epi & (kEpiBias | kEpiRes)) && p.split_k > 1) epi = -1;
   if (epi >= 0 && (epi & kEpiRes)) {
-    if (BN != 128 || obf) {
-      epi = -1;  // the TMA-fed residual path is instantiated for 128-column tiles with fp32 output
+    if ((BN != 128 && BN != 192) || obf) {
+      epi = -1;  // the TMA-fed residual path is instantiated for 128- / 192-column tiles with fp32 output
     } else {
       DGPT_REQUIRE(a->ldr % 4 == 0, "gemm(bf16): residual pitch");
       if ((rc = make_tmap_2d(&mp.r, a->residual, DGPT_F32, a->N, a->M, a->ldr, 32, 32))) return rc;
@@ -795,6 +813,24 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     }                                                                                 \
     TC_EPI(BN_, 1, 1, 0, 0)                                                           \
     return launch_cfg<BN_, 1, 1, -1, 0>(mp, p, sms, st);                              \
+  }
+  if (BN == 192) {  // single-CTA tiles only; the instantiations the N = 384 GEMMs of the model need, else generic
+    p.cta_group = 1;
+    const int grid = min(p.m_tiles * p.n_tiles * p.split_k, sms);
+#define TC_192(A_, B_, E_, O_, R_, C_) \
+    if (a_mn == (A_) && b_mn == (B_) && epi == (E_) && obf == (O_) && (a->a_colsum != nullptr) == ((C_) != 0)) \
+      return launch_one<192, A_, B_, (E_), O_, 1, R_, C_>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
+    TC_192(0, 0, 0, 1, 0, 0)
+    TC_192(0, 1, 0, 1, 0, 0)
+    TC_192(0, 1, 0, 0, 0, 0)
+    TC_192(1, 1, 0, 0, 0, 0)
+    TC_192(1, 1, 0, 0, 0, 1)
+#undef TC_192
+    DGPT_REQUIRE(!a->a_colsum, "gemm(bf16): a_colsum needs the plain fp32 wgrad form");
+    if (epi >= 0 && (epi & kEpiRes)) epi = -1;
+    if (!a_mn && !b_mn) return launch_one<192, 0, 0, -1, 0, 1, 0, 0>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
+    if (!a_mn && b_mn) return launch_one<192, 0, 1, -1, 0, 1, 0, 0>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
+    return launch_one<192, 1, 1, -1, 0, 1, 0, 0>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
   }
   TC_DISPATCH(128)
   TC_DISPATCH(256)

@@ -314,7 +314,9 @@ class Runner:
 
     @staticmethod
     def _splits(n_out_rows, n_out_cols, k, sm):
-        tiles = ((n_out_rows + 127) // 128) * ((n_out_cols + 127) // 128)
+        # column tile of the wgrad GEMM: 192 for N = 192 / 384 / 576 / 960, else 128 (launch_gemm_tc picks the same)
+        bn = 192 if (n_out_cols % 192 == 0 and n_out_cols % 256 != 0 and n_out_cols < 1024 and n_out_rows >= 1024) else 128
+        tiles = ((n_out_rows + 127) // 128) * ((n_out_cols + bn - 1) // bn)
         return max(1, min(sm // max(tiles, 1), k // 512))
 
     def _layer_bwd(self, li, L, nxt, g, g_other, gm, B, T, training):

@@ -71,7 +71,8 @@ def test_gemm_fp32_dropout_and_relu_aux():
     torch.testing.assert_close(y.cpu(), x * keep.view(-1) / (1 - p))
 
 
-TC_SHAPES = [(128, 128, 64), (256, 256, 128), (384, 1152, 384), (200, 80, 384), (130, 72, 200), (512, 384, 1536)]
+TC_SHAPES = [(128, 128, 64), (256, 256, 128), (384, 1152, 384), (200, 80, 384), (130, 72, 200), (512, 384, 1536),
+             (1100, 384, 128)]  # the last one: 192-column tiles (N = 384, >= 8 row tiles), ragged last row tile
 
 
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)
@@ -210,6 +211,19 @@ def test_gemm_tcgen05_relu_bit_masks(M, N):
     torch.testing.assert_close(d.float().cpu(), ref, rtol=1e-2, atol=1e-1)
     with pytest.raises(_lib.KernelError):
         ops.raw_gemm(G.float().to(DEV), W2.float().to(DEV), torch.empty(M, N, device=DEV), b_major=MAJOR_MN, relu_mask_in=mask)
+
+
+@pytest.mark.parametrize("bmaj", [MAJOR_K, MAJOR_MN])
+def test_gemm_tcgen05_192_column_tiles_bf16_out(bmaj):
+    """N = 384 with >= 8 row tiles runs 128 x 192 tiles; bf16 output splits the tile 128 + 64 columns between the
+    two epilogue warps of a quadrant."""
+    g = torch.Generator().manual_seed(192)
+    M, N, K = 1300, 384, 256
+    A, Bm = torch.randn(M, K, generator=g).bfloat16(), torch.randn(N, K, generator=g).bfloat16()
+    Bd = (Bm if bmaj == MAJOR_K else Bm.t().contiguous()).to(DEV)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.raw_gemm(A.to(DEV), Bd, out, b_major=bmaj, M=M, N=N, K=K)
+    torch.testing.assert_close(out.float().cpu(), A.float() @ Bm.float().t(), rtol=2e-2, atol=1e-1)
 
 
 def test_layernorm_fwd_bwd():

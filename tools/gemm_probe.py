@@ -34,7 +34,10 @@ R = 6
 
 
 def splits(rows, cols, k, sm=148):
-    tiles = ((rows + 127) // 128) * ((cols + 127) // 128)
+    bn = 192 if (cols % 192 == 0 and cols % 256 != 0 and cols < 1024 and rows >= 1024) else 128
+    if os.environ.get("DGPT_GEMM_BN192") == "0":
+        bn = 128
+    tiles = ((rows + 127) // 128) * ((cols + bn - 1) // bn)
     return max(1, min(sm // max(tiles, 1), k // 512))
 
 
