@@ -786,6 +786,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (BN == BN_) {                                                                    \
     if (!a_mn && !b_mn) {                                                             \
       TC_EPI(BN_, 0, 0, 0, 1)                                                         \
+      if (BN_ == 128) { TC_EPI(128, 0, 0, kEpiBias, 0) }  /* lm_head: fp32 logits, N = 80 (full blocks fast) */ \
       TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu, 1)                                       \
       TC_EPI(BN_, 0, 0, kEpiBias | kEpiRelu | kEpiMaskOut, 1)                         \
       if (BN_ == 128 && epi >= 0 && (epi & kEpiRes)) {                                \
