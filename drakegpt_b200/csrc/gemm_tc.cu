@@ -265,6 +265,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CG == 2) cluster_sync_all();  // the peer's TMEM and barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared memory / TMEM: with programmatic dependent launch it overlapped
+  // the tail of the previous kernel in the stream; from here on global memory is read and written
+  pdl_launch_dependents();
+  pdl_wait();
 
   // tile walk: with CG = 2 the pair handles pair-tiles (256 rows) and CTA rank r takes rows [128 r, 128 r + 128)
   const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
@@ -636,13 +640,17 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("DGPT_PDL"); pdl = e ? atoi(e) : 1; }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mr, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc: launch: %s", cudaGetErrorString(e));

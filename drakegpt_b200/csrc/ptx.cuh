@@ -25,6 +25,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (prologue: barriers, TMEM, descriptor prefetch) while its predecessor in the stream is still draining;
+// pdl_wait() blocks until the predecessor has completed and its memory is visible, pdl_launch_dependents() lets
+// the successor's CTAs be scheduled as soon as every CTA of this grid has called it (or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------- mbarrier ------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
