@@ -110,6 +110,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_grid_sync();  // prologue done (shared memory / TMEM only); global memory from here on
   if (warp == 2) ATS(1);
 
   if (warp == 0) {
@@ -351,6 +352,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
   if (warp == 0) {  // the loads do not depend on TMEM: issue them before the allocation and the CTA-wide barrier
     __syncwarp();
+    pdl_grid_sync();  // ... but they do read the previous kernel's output
     if (elect_one()) {
       // stage A: everything pair (0,0) needs; B: query tile 1 (pairs (1,0), (1,1)); C: key tile 1 (pair (1,1)).
       // O is only needed for D = rowsum(dO * O): O_0 lands in the Pd tile, O_1 in the store staging tile
@@ -378,6 +380,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+  if (warp != 0) pdl_grid_sync();  // (warp 0 passed it before issuing the loads)
 
   if (warp == 0) {
     // (loads were issued before the TMEM allocation, see above)
@@ -655,7 +658,7 @@ int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
   }
   AttnTcP p = make_tc_params(a);
   dim3 grid(a->Tk / QT, a->NH, a->B);
-  attn_fwd_tc_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(mq, mk, mv, p);
+  launch_pdl(attn_fwd_tc_kernel, grid, dim3(kFwdThreads), kFwdSmem, st, mq, mk, mv, p);
 #ifdef DGPT_ATTN_TS
   {
     cudaStreamSynchronize(st);
@@ -691,8 +694,8 @@ int launch_attn_bwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
   }
   AttnTcP p = make_tc_params(a);
   dim3 grid(a->NH, a->B);
-  if (p.thr) attn_bwd_tc_kernel<true><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
-  else attn_bwd_tc_kernel<false><<<grid, kBwdThreads, kBwdSmem, st>>>(mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
+  if (p.thr) launch_pdl(attn_bwd_tc_kernel<true>, grid, dim3(kBwdThreads), kBwdSmem, st, mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
+  else launch_pdl(attn_bwd_tc_kernel<false>, grid, dim3(kBwdThreads), kBwdSmem, st, mq, mk, mv, mg, mo, mdq, mdk, mdv, p);
 #ifdef DGPT_ATTN_TS
   {
     cudaStreamSynchronize(st);

@@ -145,4 +145,30 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  Kernels that begin with pdl_grid_sync() are launched through launch_pdl():
+// their CTAs may be scheduled (and run their on-chip prologue) while the previous kernel of the stream is still
+// draining; pdl_grid_sync() then waits until that kernel has completed and its writes are visible.
+// DGPT_PDL=0 turns the launch attribute off (the device-side calls are then no-ops).
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface in check_launch()
+}
+
 }  // namespace dgpt

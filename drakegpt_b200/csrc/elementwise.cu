@@ -18,6 +18,7 @@ __global__ void dropout_scale_kernel(const float* __restrict__ in, const float* 
                                      OutT* __restrict__ out, int64_t n,
                                      uint32_t thr, float inv_keep, uint64_t seed,
                                      const uint64_t* __restrict__ seed_dev, uint32_t site) {
+  pdl_grid_sync();
   if (thr && seed_dev) seed += *seed_dev;
   const int64_t nq = (n + 3) >> 2;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq;
@@ -52,6 +53,7 @@ __global__ void dropout_scale_kernel(const float* __restrict__ in, const float* 
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ tok,
                                  const float* __restrict__ pos, float* __restrict__ x, int M, int T,
                                  int C, int pos_offset) {
+  pdl_grid_sync();
   // one warp per row (grid-stride); float4 when the row pitch allows it
   const int lane = threadIdx.x & 31;
   const int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -78,6 +80,7 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float* _
 // dpos[t,c] += sum_b dx[b,t,c]  (deterministic: fixed summation order over b)
 __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B,
                                      int T, int C, int pos_offset) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * C) return;
   float acc = 0.f;
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(512) embed_bwd_tok_smem_kernel(const int64_t* 
                                                                  const float* __restrict__ dx,
                                                                  float* __restrict__ dtok, int M, int C, int V,
                                                                  int rows_per_cta) {
+  pdl_grid_sync();
   extern __shared__ float table[];  // [V][C], hit flags [V], then this CTA's token ids [rows_per_cta]
   int* hit = reinterpret_cast<int*>(table + (size_t)V * C);
   int* ids = hit + V;
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(256) ln_fwd_rows_kernel(float* __restrict__ x,
                                                           float eps, const int64_t* __restrict__ idx,
                                                           const float* __restrict__ tok, const float* __restrict__ pos,
                                                           int T, int pos_offset) {
+  pdl_grid_sync();
   constexpr int C = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(32 + 32 * kLnRows, 1) ln_bwd_stream_kernel(
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_grid_sync();  // barriers are set up; global memory from here on
   const int nblocks = (M + kLnRows - 1) / kLnRows;
   if (warp == 0) {
     if (lane == 0) {
@@ -674,6 +680,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(
     const float* __restrict__ logits, int ld, const int64_t* __restrict__ targets,
     float* __restrict__ loss_sum, DlT* __restrict__ dlogits, int ld_dl,
     const float* __restrict__ dloss, int M, int V) {
+  pdl_grid_sync();
   __shared__ float part[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = blockIdx.x * (blockDim.x >> 5) + w;
@@ -715,6 +722,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     __nv_bfloat16* __restrict__ shadow, int64_t n,
                                                     const float* __restrict__ hyper,
                                                     const int64_t* __restrict__ step, int zero_grad) {
+  pdl_grid_sync();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
   const double t = (double)(*step + 1);
   const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
@@ -761,7 +769,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
   }
 }
 
-__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) { *ctr += delta; }
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) {
+  pdl_grid_sync();
+  *ctr += delta;
+}
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                  int64_t n) {
@@ -893,10 +904,10 @@ static bool launch_ln_rows(float* x, const float* gamma, const float* beta, void
 #define LN_ROWS(NV_)                                                                                              \
   case NV_:                                                                                                       \
     if (y_dtype == DGPT_F32)                                                                                      \
-      ln_fwd_rows_kernel<float, NV_, R, EMBED><<<grid, 256, 0, st>>>(x, gamma, beta, (float*)y, mean, rstd, M, eps, idx, \
+      launch_pdl(ln_fwd_rows_kernel<float, NV_, R, EMBED>, dim3(grid), dim3(256), 0, st, x, gamma, beta, (float*)y, mean, rstd, M, eps, idx, \
                                                                      tok, pos, T, pos_offset);                   \
     else                                                                                                          \
-      ln_fwd_rows_kernel<__nv_bfloat16, NV_, R, EMBED><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)y, mean,    \
+      launch_pdl(ln_fwd_rows_kernel<__nv_bfloat16, NV_, R, EMBED>, dim3(grid), dim3(256), 0, st, x, gamma, beta, (__nv_bfloat16*)y, mean,    \
                                                                              rstd, M, eps, idx, tok, pos, T, pos_offset); \
     break;
   switch (C / 128) {
@@ -923,10 +934,9 @@ int dgpt_dropout_scale(const float* in, const float* relu_aux, void* out, int ou
   const int grid = (int)min((int64_t)kSMs * 8, (n / 4 + 255) / 256 + 1);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == DGPT_F32)
-    dropout_scale_kernel<float><<<grid, 256, 0, st>>>(in, relu_aux, (float*)out, n, thr, inv_keep, seed, seed_dev, site);
+    launch_pdl(dropout_scale_kernel<float>, dim3(grid), dim3(256), 0, st, in, relu_aux, (float*)out, n, thr, inv_keep, seed, seed_dev, site);
   else
-    dropout_scale_kernel<__nv_bfloat16>
-        <<<grid, 256, 0, st>>>(in, relu_aux, (__nv_bfloat16*)out, n, thr, inv_keep, seed, seed_dev, site);
+    launch_pdl(dropout_scale_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, in, relu_aux, (__nv_bfloat16*)out, n, thr, inv_keep, seed, seed_dev, site);
   return check_launch("dropout_scale");
 }
 
@@ -945,7 +955,7 @@ int dgpt_embed_fwd(const int64_t* idx, const float* tok, const float* pos, float
   const int64_t total = (int64_t)B * T * C;
   if (total == 0) return DGPT_OK;
   const int grid = (int)min((int64_t)kSMs * 8, ((int64_t)B * T + 7) / 8);
-  embed_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, tok, pos, x, B * T, T, C, pos_offset);
+  launch_pdl(embed_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, idx, tok, pos, x, B * T, T, C, pos_offset);
   return check_launch("embed_fwd");
 }
 
@@ -954,7 +964,7 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
   DGPT_DEVICE_OR_RETURN();
   if ((int64_t)B * T == 0) return DGPT_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dpos) embed_bwd_pos_kernel<<<ceil_div((int64_t)T * C, 256), 256, 0, st>>>(dx, dpos, B, T, C, pos_offset);
+  if (dpos) launch_pdl(embed_bwd_pos_kernel, dim3(ceil_div((int64_t)T * C, 256)), dim3(256), 0, st, dx, dpos, B, T, C, pos_offset);
   const int M_ = B * T;
   const int ctas_ = min(kSMs, ceil_div(M_, 32));
   const size_t table_bytes = ((size_t)V * C + V + ceil_div(M_, ctas_)) * sizeof(float);
@@ -969,7 +979,7 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
     const int M = B * T;
     const int ctas = min(kSMs, ceil_div(M, 32));
     const int rows_per_cta = ceil_div(M, ctas);
-    embed_bwd_tok_smem_kernel<<<ceil_div(M, rows_per_cta), 384, table_bytes, st>>>(idx, dx, dtok, M, C, V, rows_per_cta);
+    launch_pdl(embed_bwd_tok_smem_kernel, dim3(ceil_div(M, rows_per_cta)), dim3(384), table_bytes, st, idx, dx, dtok, M, C, V, rows_per_cta);
   } else {
     dim3 grid(V, ceil_div(C, 512));
     embed_bwd_tok_kernel<<<grid, 256, 0, st>>>(idx, dx, dtok, B * T, C);
@@ -1041,9 +1051,9 @@ int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma
       cudaFuncSetAttribute(ln_bwd_stream_kernel<NV, DyT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    ln_bwd_stream_kernel<NV, DyT, MT><<<grid, 32 + 32 * kLnRows, smem, st>>>(                                        \
-        (const DyT*)dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (MT*)dxm, dxm_colsum, thr, ik, seed, seed_dev, \
-        site, M, C);                                                                                                 \
+    launch_pdl(ln_bwd_stream_kernel<NV, DyT, MT>, dim3(grid), dim3(32 + 32 * kLnRows), smem, st,                    \
+               (const DyT*)dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (MT*)dxm, dxm_colsum, thr, ik, seed, seed_dev, \
+               site, M, C);                                                                                          \
   } while (0)
 #define LN_STREAM_T(NV)                                                                \
   do {                                                                                 \
@@ -1109,15 +1119,15 @@ int dgpt_cross_entropy(const float* logits, int ld, const int64_t* targets, floa
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(M, 8);
   if (dl_dtype == DGPT_F32)
-    cross_entropy_kernel<float><<<grid, 256, 0, st>>>(logits, ld, targets, loss_sum, (float*)dlogits, ld_dl, dloss, M, V);
+    launch_pdl(cross_entropy_kernel<float>, dim3(grid), dim3(256), 0, st, logits, ld, targets, loss_sum, (float*)dlogits, ld_dl, dloss, M, V);
   else
-    cross_entropy_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(logits, ld, targets, loss_sum, (__nv_bfloat16*)dlogits, ld_dl, dloss, M, V);
+    launch_pdl(cross_entropy_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, logits, ld, targets, loss_sum, (__nv_bfloat16*)dlogits, ld_dl, dloss, M, V);
   return check_launch("cross_entropy");
 }
 
 int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream) {
   DGPT_DEVICE_OR_RETURN();
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
+  launch_pdl(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, ctr, delta);
   return check_launch("counter_add");
 }
 
@@ -1130,8 +1140,8 @@ int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n, 
                    (((uintptr_t)shadow) & 7) == 0,
                "adamw: arenas must be 16-byte aligned");
   const int grid = (int)min((int64_t)kSMs * 8, (n / 4 + 255) / 256 + 1);
-  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)shadow, n, hyper, step, zero_grad);
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint64_t*>(step), 1ull);
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)shadow, n, hyper, step, zero_grad);
+  launch_pdl(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, reinterpret_cast<uint64_t*>(step), 1ull);
   return check_launch("adamw");
 }
 

@@ -647,10 +647,8 @@ static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DGPT_PDL"); pdl = e ? atoi(e) : 1; }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mr, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc: launch: %s", cudaGetErrorString(e));

@@ -1,5 +1,6 @@
 // Error plumbing, device gate and small host-side utilities of the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -22,6 +23,15 @@ int check_launch(const char* what) {
     return DGPT_E_LAUNCH;
   }
   return DGPT_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DGPT_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 
 // One probe per device per process; there is no CPU fallback behind this gate.
