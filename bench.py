@@ -137,8 +137,8 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------- #
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (ncu --set full capture,
-# profiles/r1_gemm_ffn1_metrics.txt; 13.80 MB read + 1.24 MB written: inputs from HBM, the 50 MB bf16 output is still L2-resident when the kernel ends)
-ROOFLINE_TRAFFIC_BYTES = 15.04e6
+# profiles/r1_gemm_ffn1_metrics.txt; 13.80 MB read + 1.69 MB written: inputs from HBM, the 50 MB bf16 output is still L2-resident when the kernel ends)
+ROOFLINE_TRAFFIC_BYTES = 15.49e6
 
 
 def time_gemm_roofline(dev, pk):
