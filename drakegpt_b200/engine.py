@@ -260,8 +260,9 @@ class Runner:
         """Backward of the last ``forward(..., save=True)``; gradients are ACCUMULATED into the flat arena.
 
         ``reducer`` (parallel.GradAllReducer built by ``make_reducer``) is told after the lm_head, after
-        every block and after the embeddings that the next gradient bucket is final, so the data-parallel
-        all-reduce of that slice overlaps the rest of the backward pass.
+        every block and after the embeddings that the next gradient bucket is final; in its overlapped mode the
+        all-reduce of that slice then runs beside the rest of the backward pass (default: one all-reduce in
+        ``reducer.finish()``, see parallel.GradAllReducer).
         """
         sp = self.spec
         if sp["kind"] != "TransformerLM":

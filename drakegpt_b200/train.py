@@ -11,8 +11,8 @@ Documented differences:
     pass ``--reference-batching`` to reproduce the reference behaviour;
   * wandb is optional (``--wandb``; no network on the GPU boxes, SURVEY Q15);
   * the optimizer is the fused flat AdamW and, for TransformerLM, the whole step is a CUDA graph;
-    under ``torchrun`` the step is data-parallel (one process per GPU, NCCL gradient all-reduce
-    overlapped with backward);
+    under ``torchrun`` the step is data-parallel (one process per GPU, one NCCL gradient all-reduce per
+    step inside the captured graph; ``DGPT_DP_OVERLAP=1`` selects the bucketed, overlapped schedule);
   * ``--synthetic N`` trains on a synthetic N-character corpus when ../data is absent (the Kaggle
     corpus cannot be downloaded here).
 """
