@@ -26,6 +26,8 @@ S = dict(vocab_size=80, embedding_dim=384, context_length=256, num_heads=6, num_
          batch_size=64, base_lr=3e-4)
 FLOP_PER_TOKEN = 3 * (6 * (24 * 384 ** 2 + 2 * (256 + 1) * 384) + 2 * 384 * 80)  # 67 438 080
 METRIC = "train_tokens_per_sec_TransformerLM_scaled"
+WORKLOAD = ("TransformerLM_scaled train step: V=80 C=384 T=256 NH=6 L=6 dropout=0.2, "
+            "AdamW lr 3e-4 betas (0.9,0.95) wd 0.01; 64x256 tokens per GPU per step")
 
 
 def peaks():
@@ -127,7 +129,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": spt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TransformerLM_scaled train step (V=80,C=384,T=256,NH=6,L=6,p=0.2), CPU sample batch 8x256"},
+            "config": {"workload": WORKLOAD, "global_batch": S["batch_size"], "seq_len": S["context_length"],
+                       "parallelism": f"cpu{threads}", "sample": f"each timed step is {B}x256 tokens of that workload"},
             "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -262,8 +265,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if r.mode == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "TransformerLM_scaled train step: V=80 C=384 T=256 NH=6 L=6 dropout=0.2, "
-                                   "AdamW lr 3e-4 betas (0.9,0.95) wd 0.01; 64x256 tokens per GPU per step",
+            "config": {"workload": WORKLOAD,
                        "global_batch": world * B, "seq_len": T, "parallelism": f"dp{world}",
                        "cuda_graph": step is not None,
                        "l2": "no explicit flush: each step streams > 1 GB of activations through a 126 MB L2"},

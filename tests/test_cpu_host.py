@@ -125,3 +125,19 @@ def test_gradient_bucket_plan_covers_arena():
     assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
     with pytest.raises(ValueError):
         bucket_ranges(slots, n_live, groups[:-1])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints one JSON line with the
+    contract's keys, on the GPU arm's metric / unit / workload."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_tokens_per_sec_TransformerLM_scaled"
+    assert line["unit"] == "tokens/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["config"]["workload"].startswith("TransformerLM_scaled train step") and line["config"]["seq_len"] == 256
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
