@@ -13,8 +13,11 @@
 
 using namespace dgpt::ptx;
 
-template <int BN>
-__global__ void __launch_bounds__(128, 1) mma_rate(int mode, int groups, long long* out) {
+// MODE is a template parameter on purpose: with run-time mode tests the compiler emits several predicated UTCHMMA
+// variants per MMA, and a predicated-off UTCHMMA still costs issue time (the numbers of ALL modes then change).
+template <int BN, int MODE>
+__global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* out) {
+  constexpr int mode = MODE;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
@@ -44,6 +47,37 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int mode, int groups, long lo
         tc_fence_after();
       }
       const uint64_t da0 = make_smem_desc_sw128(sa, 16, 1024), db0 = make_smem_desc_sw128(sb, 16, 1024);
+      if (mode == 5 || mode == 6) {
+        // bookkeeping sliced between the MMA issues of the group (the tensor pipe buffers about one MMA):
+        //   5: MMA0 | ready-barrier wait + fence | MMA1 MMA2 MMA3 | commit
+        //   6: MMA0 | commit (of the previous group) | MMA1 | ready-barrier wait + fence | MMA2 MMA3
+        if (elect_one()) tc_mma_bf16(tmem, da0, db0, idesc, g ? 1u : 0u);
+        __syncwarp();
+        if (mode == 5) {
+          mbar_wait(&bars[2], 0);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 1; k < 4; ++k) tc_mma_bf16(tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, 1u);
+            tc_commit(&bars[1]);
+          }
+          __syncwarp();
+        } else {
+          if (elect_one()) {
+            if (g) tc_commit(&bars[1]);
+            tc_mma_bf16(tmem, da0 + 2, db0 + 2, idesc, 1u);
+          }
+          __syncwarp();
+          mbar_wait(&bars[2], 0);
+          tc_fence_after();
+          if (elect_one()) {
+            tc_mma_bf16(tmem, da0 + 4, db0 + 4, idesc, 1u);
+            tc_mma_bf16(tmem, da0 + 6, db0 + 6, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -79,23 +113,22 @@ int main() {
   cudaMalloc(&out, 64);
   const int groups = 512;
   const int smem = 4 * 49152;
-  cudaFuncSetAttribute(mma_rate<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(mma_rate<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+
   const char* names[] = {"back-to-back", "commit every 4", "commit+wait every 4", "commit + ready-barrier wait + fence every 4",
-                         "back-to-back, A from TMEM (TS mode)"};
-  for (int bn : {128, 256}) {
-    for (int mode = 0; mode < 5; ++mode) {
-      if (mode == 4 && bn == 256) continue;  // TMEM: accumulator 256 columns + A above it
-      for (int rep = 0; rep < 2; ++rep) {
-        if (bn == 128) mma_rate<128><<<148, 128, smem>>>(mode, groups, out);
-        else mma_rate<256><<<148, 128, smem>>>(mode, groups, out);
-      }
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
-      long long h;
-      cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
-      printf("N=%d %-44s %7.1f cycles per 4-MMA k-block (floor %d)\n", bn, names[mode], (double)h / groups, 2 * bn);
-    }
-  }
+                         "back-to-back, A from TMEM (TS mode)", "MMA0 | wait+fence | MMA1-3 | commit",
+                         "MMA0 | commit(prev) | MMA1 | wait+fence | MMA2-3"};
+  auto run = [&](auto kern, int bn, int mode) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 2; ++rep) kern<<<148, 128, smem>>>(groups, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return; }
+    long long h;
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+    printf("N=%d %-52s %7.1f cycles per 4-MMA k-block (floor %d)\n", bn, names[mode], (double)h / groups, 2 * bn);
+  };
+  run(mma_rate<128, 0>, 128, 0); run(mma_rate<128, 1>, 128, 1); run(mma_rate<128, 2>, 128, 2); run(mma_rate<128, 3>, 128, 3);
+  run(mma_rate<128, 4>, 128, 4); run(mma_rate<128, 5>, 128, 5); run(mma_rate<128, 6>, 128, 6);
+  run(mma_rate<256, 0>, 256, 0); run(mma_rate<256, 1>, 256, 1); run(mma_rate<256, 2>, 256, 2); run(mma_rate<256, 3>, 256, 3);
+  run(mma_rate<256, 5>, 256, 5); run(mma_rate<256, 6>, 256, 6);
   return 0;
 }
