@@ -93,6 +93,9 @@ class Runner:
         self.base_seed = 0
         self.opt = None
         self._cache = None
+        self._fwd_gen = 0      # bumped by every forward(save=True): the saved activations belong to that call only
+        self._flat_gen = 0     # bumped whenever the parameter arena is rebuilt (keys the captured decode graphs)
+        self._sm = ops.sm_count()
 
     # ------------------------------------------------------------------ #
     # plumbing
@@ -109,6 +112,8 @@ class Runner:
                 self.opt.flat = self.flat
             self.device = self.flat.device
             self._ws = {}
+            self._flat_gen += 1
+            self.__dict__.pop("_decode_graphs", None)  # captured against the old arena
 
     def buf(self, key, shape, dtype=None, zero=False):
         dtype = self.at if dtype is None else dtype
@@ -157,6 +162,9 @@ class Runner:
         idx = idx.contiguous()
         tok = self.f(sp["tok"])
         V = tok.shape[0]
+        if save:
+            self._fwd_gen += 1
+            self._saved_shape = (B, T)
         if sp["kind"] == "BigramLM":
             logits = self.buf("logits", (M, V), torch.float32)
             ops.raw_embed_fwd(idx, tok, None, logits.view(B, T, V))
@@ -180,6 +188,20 @@ class Runner:
             if xin.dtype != self.at:
                 xin = ops.raw_dropout_scale(x, self.buf("x_last_at", x.shape))
             self._x_last = xin
+            Cin = xin.shape[1]
+            if self.mode == "bf16" and ops.lmhead_ce_supported(V, Cin) and (targets is not None or want_logits):
+                # fused LM head + cross-entropy (src/model.py:599-607): the logits row of every token stays in TMEM;
+                # fp32 logits are written only when the caller wants them (the training step does not)
+                logits = self.buf("logits", (M, V), torch.float32) if want_logits else None
+                loss = dl = None
+                if targets is not None:
+                    loss = self.buf("loss", (1,), torch.float32)
+                    loss.zero_()
+                    if save:
+                        dl = self.buf("dlogits", (M, (V + 7) // 8 * 8), self.at, zero=True)
+                ops.raw_lmhead_ce(xin, self.w(sp["lm"][0]), self.f(sp["lm"][1]),
+                                  None if targets is None else targets.contiguous().view(-1), loss, dl, logits)
+                return logits, (None if loss is None else loss.view(()))
             logits = self.buf("logits", (M, V), torch.float32)
             self._gemm(xin, self.w(sp["lm"][0]), logits, bias=self.f(sp["lm"][1]))
         loss = None
@@ -256,8 +278,13 @@ class Runner:
     # ------------------------------------------------------------------ #
     # backward (TransformerLM / ResidualBlock2 structure)
     # ------------------------------------------------------------------ #
-    def backward(self, idx, training=True, reducer=None):
+    def backward(self, idx, training=True, reducer=None, fwd_gen=None):
         """Backward of the last ``forward(..., save=True)``; gradients are ACCUMULATED into the flat arena.
+
+        The saved activations live in per-shape workspaces shared by every call, so only the LATEST
+        ``forward(save=True)`` can be differentiated: ``fwd_gen`` (the value of ``self._fwd_gen`` right after
+        the forward the caller wants to differentiate) makes a stale backward raise instead of silently using
+        another call's activations.
 
         ``reducer`` (parallel.GradAllReducer built by ``make_reducer``) is told after the lm_head, after
         every block and after the embeddings that the next gradient bucket is final; in its overlapped mode the
@@ -268,11 +295,18 @@ class Runner:
         if sp["kind"] != "TransformerLM":
             raise KernelError("Runner.backward implements the TransformerLM block structure; smaller models "
                               "train through the autograd Functions in ops.py")
+        if fwd_gen is not None and fwd_gen != self._fwd_gen:
+            raise KernelError("backward of a stale forward: a later forward(save=True) on this model overwrote the "
+                              "saved activations (one forward/backward pair at a time per model; gradient "
+                              "accumulation must run forward+backward per micro-batch)")
         B, T = idx.shape
+        if getattr(self, "_saved_shape", None) != (B, T):
+            raise KernelError(f"backward for a ({B},{T}) batch but the last forward(save=True) saw "
+                              f"{getattr(self, '_saved_shape', None)}")
         M = B * T
         tok = self.f(sp["tok"])
         V, C = tok.shape
-        sm = 148
+        sm = self._sm
         dl = self.buf("dlogits", (M, (V + 7) // 8 * 8), self.at, zero=True)
         x_last = self._x_last
         # lm_head: dW = dl^T x, db = colsum(dl), dx = dl W
@@ -325,7 +359,7 @@ class Runner:
         M, C = g.shape
         NH, H = L["NH"], L["H"]
         D = NH * H
-        sm = 148
+        sm = self._sm
         tag = lambda n: f"L{li}.{n}"  # noqa: E731
         at = self.at
         F = self.f(L["ffn"][1]).shape[0]
@@ -368,10 +402,12 @@ class Runner:
         dqkv = self.buf("dqkv", (M, 3 * D))
         q3, d3 = qkv.view(B, T, 3 * D), dqkv.view(B, T, 3 * D)
         q, k, v = q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:]
-        nbytes = ops.attn_bwd_scratch_bytes(q, k, NH, H)
+        a3, g3 = att.view(B, T, D), datt.view(B, T, D)
+        dq, dk, dv = d3[:, :, :D], d3[:, :, D:2 * D], d3[:, :, 2 * D:]
+        nbytes = ops.attn_bwd_scratch_bytes(q, k, v, a3, lse, g3, dq, dk, dv, NH, H)
         scratch = self.buf("attn_scratch", ((nbytes + 3) // 4,), torch.float32)
-        ops.raw_attn_bwd(q, k, v, att.view(B, T, D), lse, datt.view(B, T, D), d3[:, :, :D], d3[:, :, D:2 * D],
-                         d3[:, :, 2 * D:], scratch, NH, H, H ** -0.5, self._drop(L["p_attn"], 4 * li, training))
+        ops.raw_attn_bwd(q, k, v, a3, lse, g3, dq, dk, dv, scratch, NH, H, H ** -0.5,
+                         self._drop(L["p_attn"], 4 * li, training))
         # ---- QKV projection ----
         self._gemm(dqkv, xn1, self.g(L["qkv"]).view(3 * D, C), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
                    split_k=self._splits(3 * D, C, M, sm))
@@ -401,7 +437,7 @@ class Runner:
         """
         if self.opt is None:
             raise KernelError("call configure_optimizer() first")
-        _, loss = self.forward(idx, targets, training=True, save=True)
+        _, loss = self.forward(idx, targets, training=True, save=True, want_logits=False)
         self.backward(idx, training=True, reducer=reducer)
         if reducer is not None:
             reducer.finish()
@@ -525,7 +561,7 @@ class Runner:
             if not use_graphs:
                 step_kernels(t, sampling, greedy)
                 continue
-            key = (Bn, t, sampling, bool(greedy), id(self.flat))
+            key = (Bn, t, sampling, bool(greedy), self._flat_gen)
             g = graphs.get(key)
             if g is None:
                 step_kernels(t, sampling, greedy)  # warm-up: allocates workspaces, loads kernels

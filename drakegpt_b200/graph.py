@@ -45,3 +45,40 @@ class GraphedTrainStep:
         self.graph.replay()
         self.runner.opt.t += 1
         return self.loss
+
+
+class GraphedEvalStep:
+    """CUDA-graph capture of the evaluation forward (reference: src/train.py:61-75).
+
+    One replay = eval-mode forward of a (B, T) batch + ``loss_sum += loss`` on the device, so a whole split of
+    ``evaluate_loss`` costs one graph replay per batch and ONE host sync, instead of the reference's
+    ``loss.item()`` per batch.  The batch lives in static device buffers filled by ``copy_`` before each replay.
+    """
+
+    def __init__(self, runner, batch_size, seq_len):
+        self.runner = runner
+        dev = runner.device
+        self.idx = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
+        self.targets = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
+        self.loss_sum = torch.zeros((), device=dev, dtype=torch.float32)
+        self.flat_gen = runner._flat_gen
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            runner.forward(self.idx, self.targets, training=False, want_logits=False)  # allocate workspaces, load kernels
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _, loss = runner.forward(self.idx, self.targets, training=False, want_logits=False)
+            self.loss_sum.add_(loss)
+        self.loss_sum.zero_()
+
+    def reset(self):
+        self.loss_sum.zero_()
+
+    def step(self, idx, targets):
+        self.idx.copy_(idx, non_blocking=True)
+        self.targets.copy_(targets, non_blocking=True)
+        self.runner.flat.refresh_shadow()  # parameters touched by torch since the capture (e.g. load_state_dict)
+        self.graph.replay()

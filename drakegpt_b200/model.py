@@ -65,7 +65,7 @@ class _RunnerLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, idx, targets, training, *params):
         logits, loss = runner.forward(idx, targets, training=training, save=True)
-        ctx.runner, ctx.training, ctx.idx = runner, training, idx
+        ctx.runner, ctx.training, ctx.idx, ctx.fwd_gen = runner, training, idx, runner._fwd_gen
         ctx.names = [n for n, _ in runner.model.named_parameters()]
         ctx.mark_non_differentiable(logits)
         return logits.clone(), loss.clone()
@@ -75,7 +75,7 @@ class _RunnerLoss(torch.autograd.Function):
         r = ctx.runner
         keep = r.flat.g.clone()
         r.flat.g.zero_()
-        r.backward(ctx.idx, training=ctx.training)
+        r.backward(ctx.idx, training=ctx.training, fwd_gen=ctx.fwd_gen)
         fresh = r.flat.g * dloss
         r.flat.g.copy_(keep)
         grads = []

@@ -106,13 +106,15 @@ class _PackedAttention(nn.Module):
                         missing_keys.append(key)
                     continue
                 src = state_dict[key]
-                dst = self.qkv.data[_QKV_NAMES.index(name), j]
-                if tuple(src.shape) != tuple(dst.shape):
+                which = _QKV_NAMES.index(name)
+                if tuple(src.shape) != tuple(self.qkv.shape[2:]):
                     error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(src.shape)} "
-                                      f"from checkpoint, the shape in current model is {tuple(dst.shape)}.")
+                                      f"from checkpoint, the shape in current model is {tuple(self.qkv.shape[2:])}.")
                     continue
                 with torch.no_grad():
-                    dst.copy_(src)
+                    # through the Parameter (not .data): bumps qkv._version, which is what tells
+                    # optim.FlatParams.refresh_shadow that the bf16 shadow of this tensor is stale
+                    self.qkv[which, j].copy_(src)
         if strict:
             children = tuple(prefix + n + "." for n in self._modules)
             for key in state_dict:

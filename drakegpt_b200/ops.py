@@ -43,6 +43,12 @@ def _need_cuda(*ts):
                 "drakegpt_b200 ops need CUDA tensors (there is no CPU fallback); got a tensor on " + str(t.device))
 
 
+def sm_count():
+    """SM count of the current device (dgpt_sm_count); 148 on a B200."""
+    n = int(_lib.lib().dgpt_sm_count())
+    return n if n > 0 else 148
+
+
 def next_seed():
     """Fresh 63-bit dropout seed from torch's CPU generator (so torch.manual_seed controls it)."""
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
@@ -126,20 +132,30 @@ def raw_attn_fwd(q, k, v, o, lse, NH, H, scale, dropout=None):
     return o
 
 
-def attn_bwd_scratch_bytes(q, k, NH, H):
-    a = AttnArgs()
-    a.dtype, a.B, a.NH, a.H, a.Tq, a.Tk = _DT[q.dtype], q.shape[0], NH, H, q.shape[1], k.shape[1]
-    return int(_lib.lib().dgpt_attn_bwd_scratch_bytes(C.byref(a)))
-
-
-def raw_attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, scale, dropout=None):
-    _need_cuda(q, k, v, o, d_o, dq, dk, dv)
+def _attn_bwd_args(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, scale, dropout):
     a = _attn_args(q, k, v, o, lse, NH, H, scale, dropout)
     a.d_o, a.dq, a.dk, a.dv, a.scratch = _p(d_o), _p(dq), _p(dk), _p(dv), _p(scratch)
     a.do_bs, a.do_rs = d_o.stride(0), d_o.stride(1)
     a.dq_bs, a.dq_rs = dq.stride(0), dq.stride(1)
     a.dk_bs, a.dk_rs = dk.stride(0), dk.stride(1)
     a.dv_bs, a.dv_rs = dv.stride(0), dv.stride(1)
+    return a
+
+
+def attn_bwd_scratch_bytes(q, k, v, o, lse, d_o, dq, dk, dv, NH, H):
+    """Scratch bytes dgpt_attn_bwd needs for exactly these operands (16 on the tcgen05 path, which keeps the
+    T x T tiles on chip; B*NH*Tq*Tk*8 on the exact path).  Takes the real tensors: the kernel choice depends on
+    their dtype, alignment and strides, not only on the shape."""
+    a = _attn_bwd_args(q, k, v, o, lse, d_o, dq, dk, dv, None, NH, H, 1.0, None)
+    return int(_lib.lib().dgpt_attn_bwd_scratch_bytes(C.byref(a)))
+
+
+def raw_attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, scale, dropout=None):
+    _need_cuda(q, k, v, o, d_o, dq, dk, dv)
+    a = _attn_bwd_args(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, scale, dropout)
+    need = int(_lib.lib().dgpt_attn_bwd_scratch_bytes(C.byref(a)))
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        raise _lib.KernelError(f"attn_bwd: scratch of {need} bytes required")
     check(_lib.lib().dgpt_attn_bwd(C.byref(a), _stream()), "dgpt_attn_bwd")
 
 
@@ -216,6 +232,21 @@ def raw_cross_entropy(logits, targets, loss_sum, dlogits=None, dloss=None, M=Non
                                         _DT[dlogits.dtype] if dlogits is not None else 0,
                                         dlogits.stride(0) if dlogits is not None else 0, _p(dloss), M, V,
                                         _stream()), "dgpt_cross_entropy")
+
+
+def lmhead_ce_supported(V, K):
+    return bool(_lib.lib().dgpt_lmhead_ce_supported(int(V), int(K)))
+
+
+def raw_lmhead_ce(x, w, bias, targets=None, loss_sum=None, dlogits=None, logits=None, dloss=None):
+    """Fused LM head + cross-entropy (tensor mode), see dgpt_lmhead_ce: x bf16 [M,K], w bf16 [V,K]."""
+    _need_cuda(x, w)
+    M, K = x.shape
+    V = w.shape[0]
+    check(_lib.lib().dgpt_lmhead_ce(_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), _p(targets), _p(loss_sum),
+                                    _p(dlogits), dlogits.stride(0) if dlogits is not None else 0,
+                                    _p(logits), logits.stride(0) if logits is not None else 0, _p(dloss), M, V, K,
+                                    _stream()), "dgpt_lmhead_ce")
 
 
 def raw_adamw(p, g, m, v, shadow, hyper, step, zero_grad=True, n=None):
@@ -343,7 +374,8 @@ class _Attention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         d3 = dqkv.view(B, T, 3 * NH * H)
         dq, dk, dv = d3[:, :, : NH * H], d3[:, :, NH * H: 2 * NH * H], d3[:, :, 2 * NH * H:]
-        scratch = torch.empty((attn_bwd_scratch_bytes(q, k, NH, H) + 3) // 4, device=qkv.device, dtype=torch.float32)
+        nb = attn_bwd_scratch_bytes(q, k, v, o, lse, d_o, dq, dk, dv, NH, H)
+        scratch = torch.empty((nb + 3) // 4, device=qkv.device, dtype=torch.float32)
         raw_attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, H ** -0.5, drop)
         dx = dw = None
         if ctx.needs_input_grad[0]:

@@ -14,7 +14,10 @@ Documented differences:
     under ``torchrun`` the step is data-parallel (one process per GPU, one NCCL gradient all-reduce per
     step inside the captured graph; ``DGPT_DP_OVERLAP=1`` selects the bucketed, overlapped schedule);
   * ``--synthetic N`` trains on a synthetic N-character corpus when ../data is absent (the Kaggle
-    corpus cannot be downloaded here).
+    corpus cannot be downloaded here);
+  * ``--checkpoint-every N`` / ``--resume PATH`` save and restore the full training state (weights, Adam
+    moments and step, CyclicLR position, iteration, dropout counter, sampler RNG) -- absent upstream, which
+    saves only ``state_dict`` at the end (src/train.py:181-183).
 """
 import argparse
 import os
@@ -70,10 +73,30 @@ def build_model(model_name, scale, params, scale_params, vocab_size, device):
 def evaluate_loss(train_data, val_data, model, eval_iters, context_length, batch_size, device):
     """Mean loss over eval_iters random batches of each split (src/train.py:61-75).
 
-    Losses stay on the device and are averaged there: one host sync per split instead of one per batch.
+    Same batches as the reference (``get_batch`` consumes the torch CPU generator identically).  Losses stay
+    on the device: one host sync per split instead of one ``loss.item()`` per batch, and for the fused
+    TransformerLM engine the eval forward + loss accumulation is one CUDA-graph replay per batch
+    (``graph.GraphedEvalStep``).
     """
     out = {}
+    graphed = None
+    if isinstance(model, TransformerLM) and model.precision == "bf16" and not model.training:
+        from .graph import GraphedEvalStep
+        runner = model.runner()
+        runner._reattach()
+        cache = runner.__dict__.setdefault("_eval_graphs", {})
+        key = (batch_size, context_length, runner._flat_gen)
+        graphed = cache.get(key)
+        if graphed is None:
+            graphed = cache[key] = GraphedEvalStep(runner, batch_size, context_length)
     for name, data in (("train", train_data), ("val", val_data)):
+        if graphed is not None:
+            graphed.reset()
+            for _ in range(eval_iters):
+                x, y = get_batch(data, context_length, batch_size, device)
+                graphed.step(x, y)
+            out[name] = (graphed.loss_sum / eval_iters).cpu()
+            continue
         acc = torch.zeros((), device=device)
         for _ in range(eval_iters):
             x, y = get_batch(data, context_length, batch_size, device)
@@ -107,6 +130,52 @@ def synthetic_corpus(n, seed=0):
     return "".join(alphabet[i] for i in ids.tolist())
 
 
+# --------------------------------------------------------------------------- #
+# full training state (absent upstream: src/train.py:181-183 saves the weights only)
+# --------------------------------------------------------------------------- #
+def training_state(model, runner, opt, it, sched_steps, batcher=None):
+    """Everything a bit-faithful continuation needs, as CPU tensors / plain values."""
+    flat = runner.flat
+    st = {
+        "format": "drakegpt_b200.training_state.v1",
+        "model": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
+        "adam_m": flat.m.detach().cpu().clone(), "adam_v": flat.v.detach().cpu().clone(),
+        "adam_step": int(opt.step_dev.item()), "lr": float(opt.param_groups[0]["lr"]),
+        "sched_steps": int(sched_steps), "iter": int(it),
+        "dropout_counter": int(runner.seed_dev.item()), "base_seed": int(runner.base_seed),
+        "torch_rng": torch.get_rng_state(),
+        "slots": {n: (o, k) for n, (o, k, _) in flat.slots.items()},
+    }
+    if batcher is not None:
+        st["batcher_rng"] = batcher.gen.get_state().cpu()
+    return st
+
+
+def load_training_state(st, model, runner, opt, batcher=None):
+    """Inverse of ``training_state``; returns (next iteration, scheduler steps taken)."""
+    if st.get("format") != "drakegpt_b200.training_state.v1":
+        raise ValueError("not a drakegpt_b200 training-state file")
+    model.load_state_dict(st["model"], strict=True)
+    runner._reattach()
+    flat = runner.flat
+    if {n: (o, k) for n, (o, k, _) in flat.slots.items()} != st["slots"]:
+        raise ValueError("training state was saved from a different model layout")
+    flat.m.copy_(st["adam_m"])
+    flat.v.copy_(st["adam_v"])
+    flat.g.zero_()
+    flat.refresh_shadow(force=True)
+    opt.step_dev.fill_(st["adam_step"])
+    opt.t = st["adam_step"]
+    opt.param_groups[0]["lr"] = st["lr"]
+    opt.upload()
+    runner.seed_dev.fill_(st["dropout_counter"])
+    runner.base_seed = st["base_seed"]
+    torch.set_rng_state(st["torch_rng"])
+    if batcher is not None and "batcher_rng" in st:
+        batcher.gen.set_state(st["batcher_rng"])
+    return st["iter"], st["sched_steps"]
+
+
 def main(argv=None):
     from ._lib import require_gpu
     from .parallel import init_from_env
@@ -120,6 +189,10 @@ def main(argv=None):
     parser.add_argument("--reference-batching", action="store_true", help="always batch with PARAMS (reference quirk)")
     parser.add_argument("--synthetic", type=int, default=0, help="train on a synthetic corpus of N characters")
     parser.add_argument("--wandb", action="store_true")
+    parser.add_argument("--model-dir", type=str, default=str(cfg.MODEL_DIR), help="where checkpoints are written")
+    parser.add_argument("--checkpoint-every", type=int, default=0, help="save the full training state every N iters")
+    parser.add_argument("--resume", type=str, default="", help="training-state file to continue from")
+    parser.add_argument("--generate", type=int, default=100, help="characters to sample after training")
     args = parser.parse_args(argv)
 
     torch.manual_seed(42)
@@ -152,21 +225,28 @@ def main(argv=None):
     T, B = hp["context_length"], hp["batch_size"]
     model.train()
 
-    fused = args.model == "TransformerLM"
-    sched_steps = 0
+    # ONE flat parameter arena per model: the Runner's (generation, the fused step and the optimizer all use it)
+    fused = args.model == "TransformerLM" and model.precision == "bf16"
+    runner = model.runner()
+    runner.base_seed = 42 + rank
+    opt = runner.configure_optimizer(lr=hp["base_lr"], betas=hp["betas"])
+    flat = runner.flat
+    batcher, step = None, None
     if fused:
         from .graph import GraphedTrainStep
-        runner = model.runner()
-        runner.base_seed = 42 + rank
-        opt = runner.configure_optimizer(lr=hp["base_lr"], betas=hp["betas"])
         reducer = runner.make_reducer() if world > 1 else None
         step = GraphedTrainStep(runner, B, T, reducer)
         batcher = DeviceBatcher(train_data, T, B, device, seed=42 + rank)
-    else:
-        from .optim import FlatParams, FusedAdamW
-        flat = FlatParams(model)
-        flat.attach_grads()
-        opt = FusedAdamW(flat, lr=hp["base_lr"], betas=hp["betas"])
+    elif world > 1:
+        import torch.distributed as dist
+        opt.grad_scale = 1.0 / world  # the SUM all-reduce below, averaged inside the fused AdamW
+
+    start_it, sched_steps = 0, 0
+    if args.resume:
+        st = torch.load(args.resume, map_location="cpu", weights_only=False)
+        start_it, sched_steps = load_training_state(st, model, runner, opt, batcher)
+        if rank == 0:
+            print(f"resumed {args.resume} at iteration {start_it}")
 
     run = None
     if args.wandb and rank == 0:
@@ -175,9 +255,10 @@ def main(argv=None):
         model_config.update(scheduler="CyclicLR", learning_rate=hp["base_lr"], betas=hp["betas"], batch_size=B)
         run = wandb.init(project="DrakeGPT", config=model_config, name=args.model)
 
+    name = f"{args.model}_scaled" if args.scale else args.model
     if rank == 0:
         print(f"--- Training {args.model} ---")
-    for it in range(args.iters):
+    for it in range(start_it, args.iters):
         if fused:
             x, y = batcher.next()
             step.step(x, y)
@@ -185,6 +266,8 @@ def main(argv=None):
             x, y = get_batch(train_data, T, B, device)
             _, loss = model(x, y)
             loss.backward()
+            if world > 1:  # data parallel on the autograd path: SUM the flat gradient arena across ranks
+                dist.all_reduce(flat.g[:flat.n_live], op=dist.ReduceOp.SUM)
             opt.step()
         if (it + 1) % args.eval_interval == 0:
             model.eval()
@@ -197,19 +280,26 @@ def main(argv=None):
             if rank == 0:
                 print(f"step {it + 1}: train loss {losses['train']:.4f}, val loss {losses['val']:.4f}")
             model.train()
+        if args.checkpoint_every and (it + 1) % args.checkpoint_every == 0 and rank == 0:
+            os.makedirs(args.model_dir, exist_ok=True)
+            path = os.path.join(args.model_dir, f"{name}.state.pt")
+            torch.save(training_state(model, runner, opt, it + 1, sched_steps, batcher), path)
+            print(f"saved training state {path} at iteration {it + 1}")
 
     if rank == 0:
-        print(f"--- Predicting 100 characters with {args.model} ---")
         model.eval()
-        idx = torch.zeros((1, 1), dtype=torch.long, device=device)
-        print(decode(model.generate(idx, max_new_tokens=100)[0].tolist()))
+        if args.generate > 0:
+            print(f"--- Predicting {args.generate} characters with {args.model} ---")
+            idx = torch.zeros((1, 1), dtype=torch.long, device=device)
+            print(decode(model.generate(idx, max_new_tokens=args.generate)[0].tolist()))
         if args.save:
-            os.makedirs(cfg.MODEL_DIR, exist_ok=True)
-            path = get_model_path(cfg.MODEL_DIR, args.model, args.scale)
+            os.makedirs(args.model_dir, exist_ok=True)
+            path = get_model_path(args.model_dir, args.model, args.scale)
             torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
             with open(path + ".vocab.txt", "w", encoding="utf-8") as f:  # tokenizer sidecar
                 f.write("".join(sorted(set(text))))
             print(f"saved {path}")
+    return model
 
 
 if __name__ == "__main__":

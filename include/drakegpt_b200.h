@@ -47,10 +47,16 @@ int dgpt_sm_count(void);
 
 /* ------------------------------------------------------------------------- *
  * Counter-based dropout mask shared by every kernel (forward and backward
- * regenerate it; nothing is stored):  keep(seed, site, i) =
- *   lane16(splitmix64(seed + (i/4)*0x9E3779B97F4A7C15 + (site+1)*0xD1B54A32D192ED03), i%4)
- *     >= round(p * 65536)
- * (four consecutive elements share one 64-bit hash, 16 bits each).
+ * regenerate it; nothing is stored).  Elements are taken in GROUPS of 32
+ * consecutive indices; with g = i / 32, e = i % 32:
+ *   h      = splitmix64(seed + g*0x9E3779B97F4A7C15 + (site+1)*0xD1B54A32D192ED03)
+ *   s      = (e odd) ? high32(h) : low32(h)
+ *   word   = s * MUL[e] + ADD[e]                      (mod 2^32; MUL[e] odd)
+ *   keep(seed, site, i)  <=>  word >= round(p * 2^32)
+ * MUL / ADD are the 32 per-position constants drop_mul(e) / drop_add(e) of
+ * drakegpt_b200/csrc/common.cuh (integer finalisers of e): one 64-bit hash
+ * per group, one 32-bit multiply-add per element.  The pairwise independence
+ * of the 32 positions is tested in tests/test_cpu_host.py.
  * Replaces nn.Dropout at src/model_component.py:324,376/401,434/454.
  * Every entry that takes `seed` also takes `seed_dev`: an optional DEVICE
  * uint64 added to `seed` when the kernel runs, so that a captured CUDA graph
@@ -206,6 +212,30 @@ int64_t dgpt_attn_bwd_scratch_bytes(const dgpt_attn_args* a);
 int dgpt_cross_entropy(const float* logits, int ld, const int64_t* targets, float* loss_sum,
                        void* dlogits, int dl_dtype, int ld_dl, const float* dloss, int M, int V,
                        void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused LM head + cross-entropy (tensor mode): ONE kernel for
+ *   logits = x . W^T + bias                     (src/model.py:599)
+ *   loss   = F.cross_entropy(logits, targets)   (src/model.py:604-607)
+ *   dlogits = (softmax(logits) - onehot(targets)) * dloss / M   (autograd)
+ * x: bf16 [M, ldx] (K columns used); w: bf16 [V, ldw] (the nn.Linear weight).
+ * One CTA per 128 rows: TMA -> tcgen05.mma 128 x V x 16 -> the logits row of
+ * every token stays in TMEM, is reduced there (row max, sum of exponentials)
+ * and only loss_sum[0] += sum_m (lse_m - logit[m, target_m]) / M (pre-zeroed
+ * by the caller) and the bf16 dlogits [M, ld_dl] leave the chip.
+ *   logits  (fp32 [M, ld_lg]) optional: written only when non-NULL (the API
+ *           returns logits; the training step passes NULL).
+ *   targets NULL: logits only (generation / eval without loss).
+ *   dloss   device scalar or NULL (= 1).
+ * Needs V % 16 == 0, 16 <= V <= 256, K % 64 == 0, K <= 512 and
+ * K * (256 + 2 V) bytes <= 227 KB of shared memory (dgpt_lmhead_ce_supported);
+ * other shapes use dgpt_gemm + dgpt_cross_entropy.
+ * ------------------------------------------------------------------------- */
+int dgpt_lmhead_ce_supported(int V, int K);
+int dgpt_lmhead_ce(const void* x, int ldx, const void* w, int ldw, const float* bias,
+                   const int64_t* targets, float* loss_sum, void* dlogits, int ld_dl,
+                   float* logits, int ld_lg, const float* dloss, int M, int V, int K,
+                   void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused flat AdamW (decoupled decay) over one parameter arena.

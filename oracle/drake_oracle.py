@@ -363,6 +363,22 @@ def train_steps(kind, sd, batches, lr, betas=(0.9, 0.95), dropout=0.0, training=
     return losses
 
 
+def structured_batches(seed, steps, B, T, V=80, corpus_len=65536):
+    """Seeded synthetic corpus with learnable structure (every odd token is a function of its predecessor) and
+    ``steps`` random (x, y) windows of it, y = x shifted by one like src/preprocessing.py:43-45.  Shared by the
+    golden generator (tests/golden/make_golden.py) and the GPU parity tests so both sides see identical batches."""
+    g = torch.Generator().manual_seed(seed)
+    corpus = torch.randint(0, V, (corpus_len,), generator=g)
+    corpus[1::2] = (corpus[::2] * 7 + 3) % V
+    out = []
+    for _ in range(steps):
+        ix = torch.randint(0, corpus_len - T - 1, (B,), generator=g)
+        offs = ix.unsqueeze(1) + torch.arange(T + 1).unsqueeze(0)
+        win = corpus[offs]
+        out.append((win[:, :-1].contiguous(), win[:, 1:].contiguous()))
+    return out
+
+
 def cyclic_lr(step, base_lr, max_lr, step_size_up=5):
     """torch CyclicLR 'triangular' lr after ``step`` scheduler.step() calls.
 

@@ -188,6 +188,39 @@ def scaled():
     torch.save(rec, os.path.join(HERE, "scaled_vectors.pt"))
 
 
+SCALED_CURVE = dict(cfg=dict(vocab_size=80, embedding_dim=384, context_length=256, num_heads=6, num_layers=6),
+                    init_seed=31415, batch_seed=27182, B=8, T=256, steps=200, lr=3e-4, betas=(0.9, 0.95))
+
+
+def scaled_curves():
+    """200 AdamW steps of the UNMODIFIED reference TransformerLM at the scaled shape (src/config.py:27-38,
+    step glue src/train.py:143-151), B=8 x T=256 per step, from oracle.synthetic_state_dict init:
+    one curve with dropout 0 and three torch seeds with dropout 0.2 (the seed-to-seed band)."""
+    sc = SCALED_CURVE
+    batches = O.structured_batches(sc["batch_seed"], sc["steps"], sc["B"], sc["T"])
+    out = dict(sc)
+    for p_drop, seeds in ((0.0, (0,)), (0.2, (1, 2, 3))):
+        curves = []
+        for sd_seed in seeds:
+            sd = O.synthetic_state_dict("TransformerLM", seed=sc["init_seed"], **sc["cfg"])
+            m = ref_model.TransformerLM(80, 384, 256, 6, 6, p_drop)
+            m.load_state_dict(sd, strict=True)
+            m.train()
+            torch.manual_seed(sd_seed)
+            opt = torch.optim.AdamW(m.parameters(), lr=sc["lr"], betas=sc["betas"])
+            losses = []
+            for x, y in batches:
+                _, loss = m(x, y)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+            curves.append(torch.tensor(losses, dtype=torch.float64))
+            print("scaled curve p=%.1f seed %d: %.4f -> %.4f" % (p_drop, sd_seed, losses[0], losses[-1]), flush=True)
+        out["p%.1f" % p_drop] = torch.stack(curves)
+    torch.save(out, os.path.join(HERE, "scaled_curves.pt"))
+
+
 def misc():
     out = {}
     # tokenizer on a synthetic corpus incl. non-ASCII
@@ -233,10 +266,15 @@ def misc():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python make_golden.py scaled_curves ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     checkpoints()
     train_curves()
     modules()
     scaled()
+    scaled_curves()
     misc()
     for f in sorted(os.listdir(HERE)):
         p = os.path.join(HERE, f)

@@ -190,5 +190,22 @@ def test_generate_kv_cache_and_window_slide():
         want = O.generate("TransformerLM", sd2, prompt.cpu(), 30, greedy=True)
         if precision == "fp32":
             assert torch.equal(got, want)
-        else:
-            assert (got == want).float().mean() > 0.6
+            continue
+        # bf16: teacher-forced on the oracle's sequence.  For every generated position n the model continues the
+        # TRUE prefix by one token (KV-cached decode inside the window, full-window recompute once it has slid) and
+        # must pick the oracle's token unless the oracle's own top-2 logit gap there is a near-tie (< 5e-2).
+        ctx, t0 = 16, prompt.shape[1]
+        ties = torch.zeros(want.shape, dtype=torch.bool)
+        for n in range(t0, want.shape[1]):
+            win = want[:, max(0, n - ctx):n]
+            lg, _ = O.forward("TransformerLM", sd2, win)
+            top = lg[:, -1].topk(2).values
+            ties[:, n] = (top[:, 0] - top[:, 1]) < 5e-2
+            nxt = m.generate(win.to(DEV), 1, greedy=True).cpu()[:, -1]
+            ok = (nxt == want[:, n]) | ties[:, n]
+            assert ok.all(), (n, nxt.tolist(), want[:, n].tolist(), (top[:, 0] - top[:, 1]).tolist())
+        assert ties.float().mean() < 0.2  # the exemption is the exception, not the rule
+        # free-running: identical to the oracle up to (not including) each row's first near-tie
+        for b in range(want.shape[0]):
+            first_tie = int(ties[b].nonzero()[0]) if ties[b].any() else want.shape[1]
+            assert torch.equal(got[b, :first_tie], want[b, :first_tie]), (b, first_tie)

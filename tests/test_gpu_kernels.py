@@ -306,7 +306,7 @@ def test_attention_dropout_matches_host_mask():
     ops.raw_attn_fwd(qd, kd, vd, o, lse, NH, H, H ** -0.5, drop)
     torch.testing.assert_close(o.cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
     dq, dk, dv = (torch.empty_like(qd) for _ in range(3))
-    scratch = torch.empty((ops.attn_bwd_scratch_bytes(qd, kd, NH, H) + 3) // 4, device=DEV)
+    scratch = torch.empty((ops.attn_bwd_scratch_bytes(qd, kd, vd, o, lse, go.to(DEV), dq, dk, dv, NH, H) + 3) // 4, device=DEV)
     ops.raw_attn_bwd(qd, kd, vd, o, lse, go.to(DEV), dq, dk, dv, scratch, NH, H, H ** -0.5, drop)
     for got, want in ((dq, qh.grad), (dk, kh.grad), (dv, vh.grad)):
         torch.testing.assert_close(got.cpu(), want.transpose(1, 2).reshape(B, T, NH * H), rtol=1e-3, atol=1e-5)
@@ -330,7 +330,8 @@ def test_attention_tcgen05_vs_exact(T, p):
         lse = torch.empty(B, NH, T, device=DEV)
         ops.raw_attn_fwd(q, k, v, o, lse, NH, H, H ** -0.5, drop)
         dx = torch.full((B, T, 3 * D), float("nan"), device=DEV, dtype=dt)
-        scratch = torch.empty((ops.attn_bwd_scratch_bytes(q, k, NH, H) + 3) // 4, device=DEV)
+        gd = go.to(DEV).to(dt)
+        scratch = torch.empty((ops.attn_bwd_scratch_bytes(q, k, v, o, lse, gd, dx[:, :, :D], dx[:, :, D:2 * D], dx[:, :, 2 * D:], NH, H) + 3) // 4, device=DEV)
         ops.raw_attn_bwd(q, k, v, o, lse, go.to(DEV).to(dt), dx[:, :, :D], dx[:, :, D:2 * D], dx[:, :, 2 * D:], scratch,
                          NH, H, H ** -0.5, drop)
         res[dt] = (o.float().cpu(), lse.cpu(), dx.float().cpu())
