@@ -14,10 +14,11 @@ F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
 
 EXPORTS = [
-    "dgpt_last_error", "dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count",
+    "dgpt_last_error", "dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count", "dgpt_debug_clock_probe", "dgpt_debug_clock_stamps",
     "dgpt_dropout_keep_host", "dgpt_gemm_set_cta_group", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
     "dgpt_embed_bwd", "dgpt_embed_ln_fwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
     "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_lmhead_ce", "dgpt_lmhead_ce_supported", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
+    "dgpt_ipc_export", "dgpt_ipc_open", "dgpt_ipc_close", "dgpt_dp_adamw",
 ]
 
 
@@ -65,6 +66,10 @@ def _declare(lib):
     for name in ("dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count"):
         getattr(lib, name).restype = i32
         getattr(lib, name).argtypes = []
+    lib.dgpt_debug_clock_probe.restype = i32
+    lib.dgpt_debug_clock_probe.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.dgpt_debug_clock_stamps.restype = i32
+    lib.dgpt_debug_clock_stamps.argtypes = [C.POINTER(C.c_uint64)]
     lib.dgpt_gemm_set_cta_group.restype = i32
     lib.dgpt_gemm_set_cta_group.argtypes = [i32]
     lib.dgpt_dropout_keep_host.restype = i32
@@ -86,6 +91,10 @@ def _declare(lib):
         "dgpt_lmhead_ce_supported": [i32, i32],
         "dgpt_adamw": [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp],
         "dgpt_counter_add": [vp, u64, vp],
+        "dgpt_ipc_export": [vp, vp, C.POINTER(C.c_int64)],
+        "dgpt_ipc_open": [vp, i64, C.POINTER(C.c_void_p)],
+        "dgpt_ipc_close": [vp, i64],
+        "dgpt_dp_adamw": [C.POINTER(C.c_void_p), i32, i32, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp],
         "dgpt_sample": [vp, i32, vp, i64, i32, i32, i32, i32, u64, vp, u32, vp],
     }
     for name, args in sig.items():

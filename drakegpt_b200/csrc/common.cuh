@@ -145,6 +145,28 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Effective SM clock of a kernel (DGPT_CLOCK_PROBE=1): one thread stamps clock64 and %globaltimer at kernel entry and
+// exit into a 4-word device buffer (clock_probe_buffer(), NULL when the probe is off) that the kernel receives as an
+// argument; dgpt_debug_clock_probe() returns (cycles, nanoseconds) of the last stamped kernel.
+unsigned long long* clock_probe_buffer();
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void clock_probe_begin(unsigned long long* buf) {
+  if (buf && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    buf[0] = (unsigned long long)clock64();
+    buf[1] = global_timer_ns();
+  }
+}
+__device__ __forceinline__ void clock_probe_end(unsigned long long* buf) {
+  if (buf && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    buf[2] = (unsigned long long)clock64();
+    buf[3] = global_timer_ns();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch.  Kernels that begin with pdl_grid_sync() are launched through launch_pdl():
 // their CTAs may be scheduled (and run their on-chip prologue) while the previous kernel of the stream is still

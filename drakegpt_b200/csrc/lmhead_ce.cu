@@ -121,12 +121,15 @@ lmhead_ce_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     float row_loss = 0.f;
     if (tgt >= 0) row_loss = (logf(se) + mx - vt) / (float)p.M;
-    const bool want_dl = p.dlogits != nullptr && tgt >= 0;
-    if ((want_dl || p.logits) && m < p.M) {
+    // (tcgen05.ld is warp-collective: the loop runs for every lane of the warp, only the stores are predicated on
+    // the row being inside the matrix -- the last row tile may be ragged)
+    const bool row_ok = m < p.M;
+    const bool want_dl = p.dlogits != nullptr && tgt >= 0 && row_ok;
+    if (p.dlogits != nullptr || p.logits != nullptr) {
       const float scale = (p.dloss ? p.dloss[0] : 1.f) / (float)p.M;
       const float inv = 1.f / se;
-      __nv_bfloat16* dr = p.dlogits ? p.dlogits + (int64_t)m * p.ld_dl : nullptr;
-      float* lr = p.logits ? p.logits + (int64_t)m * p.ld_lg : nullptr;
+      __nv_bfloat16* dr = want_dl ? p.dlogits + (int64_t)m * p.ld_dl : nullptr;
+      float* lr = (p.logits && row_ok) ? p.logits + (int64_t)m * p.ld_lg : nullptr;
       for (int c = 0; c < nch; ++c) {
         uint32_t r[16];
         tmem_ld16(taddr + c * 16, r);

@@ -25,6 +25,17 @@ int check_launch(const char* what) {
   return DGPT_OK;
 }
 
+unsigned long long* clock_probe_buffer() {
+  static int on = -1;
+  static unsigned long long* buf = nullptr;
+  if (on < 0) {
+    const char* e = getenv("DGPT_CLOCK_PROBE");
+    on = e ? (atoi(e) != 0) : 0;
+    if (on && cudaMalloc(&buf, 64 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; }
+  }
+  return buf;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -76,6 +87,31 @@ int dgpt_sm_count(void) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return DGPT_E_DEVICE;
   return n;
+}
+
+/* (cycles, nanoseconds) between entry and exit of CTA 0 of the last kernel launched with DGPT_CLOCK_PROBE=1 */
+int dgpt_debug_clock_probe(uint64_t* cycles, uint64_t* ns) {
+  unsigned long long h[4] = {0, 0, 0, 0};
+  unsigned long long* buf = dgpt::clock_probe_buffer();
+  if (!buf) { dgpt::set_error("clock probe is off (DGPT_CLOCK_PROBE=1 enables it)"); return DGPT_E_ARG; }
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return DGPT_E_DEVICE;
+  }
+  *cycles = h[2] - h[0];
+  *ns = h[3] - h[1];
+  return DGPT_OK;
+}
+
+/* the raw 64-word stamp buffer (words 0-3 as above, 4.. = kernel-specific phase stamps in cycles) */
+int dgpt_debug_clock_stamps(uint64_t* out64) {
+  unsigned long long* buf = dgpt::clock_probe_buffer();
+  if (!buf) { dgpt::set_error("clock probe is off (DGPT_CLOCK_PROBE=1 enables it)"); return DGPT_E_ARG; }
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(out64, buf, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return DGPT_E_DEVICE;
+  }
+  return DGPT_OK;
 }
 
 int dgpt_dropout_keep_host(uint64_t seed, uint32_t site, uint64_t index, float p) {

@@ -338,7 +338,14 @@ class Runner:
 
     def make_reducer(self, group=None):
         """Gradient buckets in the order the backward pass completes them (lm_head, blocks L-1..0, embeddings)."""
-        from .parallel import GradAllReducer, bucket_ranges
+        from .parallel import GradAllReducer, PeerAdamW, bucket_ranges
+        import os
+        import torch.distributed as dist
+        # default on the GPUs: ONE kernel for reduce-scatter + AdamW + all-gather over NVLink peer memory;
+        # DGPT_DP_MODE=nccl selects the NCCL all-reduce + replicated AdamW schedule (A/B, or no peer access)
+        if (self.opt is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+                and dist.get_backend(group) == "nccl" and os.environ.get("DGPT_DP_MODE", "peer") == "peer"):
+            return PeerAdamW(self.flat, self.opt, group)
         nl = len(self.spec["layers"])
         groups = [("lm_head.",)] + [(f"blocks.{i}.",) for i in range(nl - 1, -1, -1)]
         groups.append(("token_embedding_table.", "position_embedding_table."))
@@ -439,9 +446,12 @@ class Runner:
             raise KernelError("call configure_optimizer() first")
         _, loss = self.forward(idx, targets, training=True, save=True, want_logits=False)
         self.backward(idx, training=True, reducer=reducer)
-        if reducer is not None:
-            reducer.finish()
-        self.opt.launch(zero_grad=True)
+        if reducer is not None and getattr(reducer, "fused_optimizer", False):
+            reducer.launch_update()  # gradient reduction, AdamW and the parameter all-gather in one kernel
+        else:
+            if reducer is not None:
+                reducer.finish()
+            self.opt.launch(zero_grad=True)
         ops.raw_counter_add(self.seed_dev, 1)
         return loss
 

@@ -100,3 +100,118 @@ class GradAllReducer:
             w.wait()
         self._pending = []
         self._next = 0
+
+
+def shard_range(n_live, world, rank, align=64):
+    """Contiguous, ``align``-element aligned shard [lo, hi) of a flat arena of ``n_live`` elements owned by ``rank``.
+    The shards of ranks 0 .. world-1 tile [0, n_live) exactly (n_live is itself a multiple of ``align``)."""
+    if n_live % align != 0:
+        raise ValueError(f"arena length {n_live} is not a multiple of {align}")
+    units = n_live // align
+    base, extra = divmod(units, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo * align, hi * align
+
+
+class PeerAdamW:
+    """Data-parallel optimizer step as one kernel over NVLink peer memory (``dgpt_dp_adamw``): reduce-scatter of the
+    gradient arenas + AdamW on this rank's 1/N shard + all-gather of the updated fp32 parameters and bf16 shadows.
+
+    Takes the place of ``GradAllReducer`` + ``FusedAdamW.launch`` in the training step (same ``bucket_ready`` /
+    ``finish`` surface, plus ``launch_update``).  Construction exchanges CUDA IPC handles of the gradient, parameter,
+    shadow and flag buffers between the ranks of ``group`` (one process per GPU on one NVLink / NVSwitch node).
+    The Adam moments of this rank are only meaningful inside its shard; ``gather_moments`` reassembles the full
+    vectors (checkpointing).
+    """
+
+    fused_optimizer = True
+
+    def __init__(self, flat, opt, group=None):
+        import ctypes as C
+        from . import _lib
+        self.flat, self.opt, self.group = flat, opt, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerAdamW supports up to 8 ranks (one NVSwitch node)")
+        dev = flat.device
+        self.lo, self.hi = shard_range(flat.n_live, self.world, self.rank)
+        self.flags = torch.zeros(16, device=dev, dtype=torch.int32)
+        self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.scratch = torch.zeros(2, device=dev, dtype=torch.int32)
+        lib = _lib.lib()
+        mine = []
+        self._local = [flat.g, flat.p, flat.shadow, self.flags]
+        for t in self._local:
+            if t is None:
+                mine.append(None)
+                continue
+            h = (C.c_ubyte * 64)()
+            off = C.c_int64(0)
+            _lib.check(lib.dgpt_ipc_export(t.data_ptr(), h, C.byref(off)), "dgpt_ipc_export")
+            mine.append((bytes(h), int(off.value)))
+        torch.cuda.synchronize(dev)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened = []
+        ptrs = (C.c_void_p * (4 * self.world))()
+        for r in range(self.world):
+            for k in range(4):
+                if r == self.rank:
+                    ptrs[k * self.world + r] = None if self._local[k] is None else self._local[k].data_ptr()
+                elif everyone[r][k] is None:
+                    ptrs[k * self.world + r] = None
+                else:
+                    handle, off = everyone[r][k]
+                    out = C.c_void_p()
+                    _lib.check(lib.dgpt_ipc_open(handle, off, C.byref(out)), "dgpt_ipc_open")
+                    self._opened.append((out.value, off))
+                    ptrs[k * self.world + r] = out.value
+        self._ptrs = ptrs
+        opt.grad_scale = 1.0 / self.world
+        opt.upload()
+        dist.barrier(group=group)  # every rank has mapped every buffer before any kernel touches them
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def bucket_ready(self):
+        pass
+
+    def finish(self):
+        pass
+
+    def launch_update(self):
+        """Enqueue the fused reduce-scatter + AdamW + all-gather, then clear the local gradient arena."""
+        from . import _lib, ops
+        f, o = self.flat, self.opt
+        _lib.check(_lib.lib().dgpt_dp_adamw(self._ptrs, self.world, self.rank, f.m[self.lo:].data_ptr(),
+                                            f.v[self.lo:].data_ptr(), self.lo, self.hi, o.hyper.data_ptr(),
+                                            o.step_dev.data_ptr(), self.epoch.data_ptr(), self.scratch.data_ptr(), 0,
+                                            ops._stream()), "dgpt_dp_adamw")
+        f.g[:f.n_live].zero_()
+
+    def status(self):
+        """0 = ok; 1 / 2 = a peer never reached the first / second barrier of some step (host sync)."""
+        return int(self.scratch[1].item())
+
+    def gather_moments(self):
+        """Full-length (m, v) assembled from every rank's shard (CPU tensors on every rank)."""
+        n = self.flat.n_live
+        out = []
+        for t in (self.flat.m, self.flat.v):
+            full = t[:n].clone()
+            parts = [None] * self.world
+            dist.all_gather_object(parts, (self.lo, self.hi, t[self.lo:self.hi].cpu()), group=self.group)
+            full = full.cpu()
+            for lo, hi, x in parts:
+                full[lo:hi] = x
+            out.append(full)
+        return out
+
+    def close(self):
+        from . import _lib
+        for ptr, off in self._opened:
+            _lib.lib().dgpt_ipc_close(ptr, off)
+        self._opened = []

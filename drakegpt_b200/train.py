@@ -133,13 +133,20 @@ def synthetic_corpus(n, seed=0):
 # --------------------------------------------------------------------------- #
 # full training state (absent upstream: src/train.py:181-183 saves the weights only)
 # --------------------------------------------------------------------------- #
-def training_state(model, runner, opt, it, sched_steps, batcher=None):
-    """Everything a bit-faithful continuation needs, as CPU tensors / plain values."""
+def training_state(model, runner, opt, it, sched_steps, batcher=None, reducer=None):
+    """Everything a bit-faithful continuation needs, as CPU tensors / plain values.
+
+    Under data parallelism with the fused peer-memory optimizer (``parallel.PeerAdamW``) every rank holds the Adam
+    moments of its own shard only: pass the ``reducer`` and call this on EVERY rank (it gathers them)."""
     flat = runner.flat
+    if reducer is not None and getattr(reducer, "fused_optimizer", False):
+        adam_m, adam_v = reducer.gather_moments()
+    else:
+        adam_m, adam_v = flat.m.detach().cpu().clone(), flat.v.detach().cpu().clone()
     st = {
         "format": "drakegpt_b200.training_state.v1",
         "model": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
-        "adam_m": flat.m.detach().cpu().clone(), "adam_v": flat.v.detach().cpu().clone(),
+        "adam_m": adam_m, "adam_v": adam_v,
         "adam_step": int(opt.step_dev.item()), "lr": float(opt.param_groups[0]["lr"]),
         "sched_steps": int(sched_steps), "iter": int(it),
         "dropout_counter": int(runner.seed_dev.item()), "base_seed": int(runner.base_seed),
@@ -231,7 +238,7 @@ def main(argv=None):
     runner.base_seed = 42 + rank
     opt = runner.configure_optimizer(lr=hp["base_lr"], betas=hp["betas"])
     flat = runner.flat
-    batcher, step = None, None
+    batcher, step, reducer = None, None, None
     if fused:
         from .graph import GraphedTrainStep
         reducer = runner.make_reducer() if world > 1 else None
@@ -280,11 +287,13 @@ def main(argv=None):
             if rank == 0:
                 print(f"step {it + 1}: train loss {losses['train']:.4f}, val loss {losses['val']:.4f}")
             model.train()
-        if args.checkpoint_every and (it + 1) % args.checkpoint_every == 0 and rank == 0:
-            os.makedirs(args.model_dir, exist_ok=True)
-            path = os.path.join(args.model_dir, f"{name}.state.pt")
-            torch.save(training_state(model, runner, opt, it + 1, sched_steps, batcher), path)
-            print(f"saved training state {path} at iteration {it + 1}")
+        if args.checkpoint_every and (it + 1) % args.checkpoint_every == 0:
+            st = training_state(model, runner, opt, it + 1, sched_steps, batcher, reducer)  # collective under DP
+            if rank == 0:
+                os.makedirs(args.model_dir, exist_ok=True)
+                path = os.path.join(args.model_dir, f"{name}.state.pt")
+                torch.save(st, path)
+                print(f"saved training state {path} at iteration {it + 1}")
 
     if rank == 0:
         model.eval()

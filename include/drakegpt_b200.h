@@ -44,6 +44,10 @@ int dgpt_abi_version(void);
 /* 0 when the current CUDA device is sm_100 and the TMA driver entry point resolves. */
 int dgpt_device_check(void);
 int dgpt_sm_count(void);
+/* Diagnostics: with DGPT_CLOCK_PROBE=1 the GEMM and attention kernels stamp clock64 / %globaltimer in CTA 0;
+ * returns the cycles and nanoseconds of the last stamped kernel (effective SM clock under load). Synchronises. */
+int dgpt_debug_clock_probe(uint64_t* cycles, uint64_t* ns);
+int dgpt_debug_clock_stamps(uint64_t* out64); /* raw stamps: [0..3] entry/exit clock64 + ns, [4..63] kernel phases */
 
 /* ------------------------------------------------------------------------- *
  * Counter-based dropout mask shared by every kernel (forward and backward
@@ -253,6 +257,35 @@ int dgpt_lmhead_ce(const void* x, int ldx, const void* w, int ldw, const float* 
  * ------------------------------------------------------------------------- */
 int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n,
                const float* hyper, int64_t* step, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Data-parallel optimizer step over NVLink peer memory (one process per GPU):
+ * reduce-scatter of the gradient arenas + AdamW on this rank's 1/N shard +
+ * all-gather of the updated fp32 parameters and bf16 shadows in ONE kernel
+ * (P2P loads / stores on IPC-mapped peer arenas; two flag barriers).
+ * Replaces the gradient mean a DDP wrapper would add around
+ * src/train.py:149-151 plus optimizer.zero_grad() / AdamW.step(); the
+ * reference itself is single-process.
+ *   dgpt_ipc_export / dgpt_ipc_open / dgpt_ipc_close: map a peer process's
+ *     device buffer (handle = 64-byte cudaIpcMemHandle_t of the allocation,
+ *     offset = position of the buffer inside it).
+ *   peers: HOST array of 4*world device pointers -- g[world], p[world],
+ *     shadow[world] (may be NULL), flags[world] (each 16 x uint32, zeroed
+ *     once); entry [me] of each group is this rank's own buffer.
+ *   m, v: this rank's Adam moment shards ([hi - lo] floats); [lo, hi) is the
+ *     64-element aligned shard of the arena this rank owns.
+ *   hyper / step as dgpt_adamw (grad_scale = 1 / world for the mean);
+ *   epoch (device uint32) and scratch (device 2 x uint32, zeroed once) are the
+ *     barrier generation and {block counter, status}: status 1 / 2 = a peer
+ *     never reached the first / second barrier within ~2 s (no hang).
+ * The caller clears its gradient arena after this call (stream order).
+ * ------------------------------------------------------------------------- */
+int dgpt_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out);
+int dgpt_ipc_open(const void* handle, int64_t offset, void** ptr_out);
+int dgpt_ipc_close(void* ptr, int64_t offset);
+int dgpt_dp_adamw(const void* const* peers, int world, int me, float* m, float* v, int64_t lo,
+                  int64_t hi, const float* hyper, int64_t* step, uint32_t* epoch,
+                  uint32_t* scratch, int sms, void* stream);
 
 /* *ctr += delta on the stream (dropout seed offsets under CUDA graphs). */
 int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream);

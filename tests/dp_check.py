@@ -30,6 +30,11 @@ def run(model_sd, batches, world, rank, graphed):
         else:
             losses.append(r.train_step(x.to(dev), y.to(dev), red).clone())
     torch.cuda.synchronize()
+    if red is not None and getattr(red, "fused_optimizer", False):
+        assert red.status() == 0, f"peer barrier timed out (status {red.status()})"
+        mom_m, mom_v = red.gather_moments()  # full-length moments assembled from the shards
+        assert mom_m.shape == (r.flat.n_live,) and torch.isfinite(mom_v).all() and float(mom_v.abs().sum()) > 0
+        red.close()
     return torch.stack(losses).cpu(), {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.endswith("tril")}
 
 
@@ -61,7 +66,7 @@ def main():
                 assert num / den < 0.1, (k, float(num / den))
     dist.barrier()
     if rank == 0:
-        print("DP_CHECK_OK")
+        print(f"DP_CHECK_OK mode={os.environ.get('DGPT_DP_MODE', 'peer')}")
     dist.destroy_process_group()
 
 

@@ -214,3 +214,18 @@ def test_oracle_matches_reference_scaled_curve_prefix():
     assert all(abs(g - float(w)) <= 2e-5 * float(w) for g, w in zip(got, want)), (got, want.tolist())
     band = (gold["p0.2"].max(0).values - gold["p0.2"].min(0).values) / gold["p0.2"].mean(0)
     assert float(band.max()) < 0.03  # the reference's own seed-to-seed spread with dropout 0.2 (context for the GPU test)
+
+
+def test_peer_optimizer_shards_tile_the_arena():
+    """parallel.shard_range: 64-element aligned, contiguous, exhaustive and balanced for every world size."""
+    from drakegpt_b200.parallel import shard_range
+    n_live = 10_800_464 // 64 * 64 + 64 * 7
+    for world in (1, 2, 3, 4, 8):
+        rs = [shard_range(n_live, world, r) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == n_live
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(lo % 64 == 0 and hi % 64 == 0 and hi > lo for lo, hi in rs)
+        sizes = [hi - lo for lo, hi in rs]
+        assert max(sizes) - min(sizes) <= 64
+    with pytest.raises(ValueError):
+        shard_range(100, 2, 0)

@@ -95,7 +95,7 @@ def test_evaluate_loss_equals_oracle_on_the_same_windows(precision, B, T, cfg, t
     # a second call reuses the captured graph and sees parameter updates made in between
     if precision == "bf16":
         with torch.no_grad():
-            m.lm_head.bias.add_(1.0)
+            m.lm_head.weight.mul_(0.5)  # a GEMM weight: the captured graph must see the re-cast bf16 shadow
         torch.manual_seed(1234)
         again = train.evaluate_loss(tr, va, m, iters, T, B, torch.device(DEV))
         assert abs(float(again["train"]) - float(got["train"])) > 1e-3
