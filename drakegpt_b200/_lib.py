@@ -19,6 +19,8 @@ EXPORTS = [
     "dgpt_embed_bwd", "dgpt_embed_ln_fwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
     "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_lmhead_ce", "dgpt_lmhead_ce_supported", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
     "dgpt_ipc_export", "dgpt_ipc_open", "dgpt_ipc_close", "dgpt_dp_adamw",
+    "dgpt_decode_attn", "dgpt_decode_persistent", "dgpt_decode_persistent_scratch_floats",
+    "dgpt_decode_persistent_max_batch",
 ]
 
 
@@ -91,6 +93,9 @@ def _declare(lib):
         "dgpt_lmhead_ce_supported": [i32, i32],
         "dgpt_adamw": [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp],
         "dgpt_counter_add": [vp, u64, vp],
+        "dgpt_decode_attn": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, f32, vp],
+        "dgpt_decode_persistent": [C.POINTER(C.c_void_p), i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                   i32, i32, i32, i32, u64, vp, i32, vp],
         "dgpt_ipc_export": [vp, vp, C.POINTER(C.c_int64)],
         "dgpt_ipc_open": [vp, i64, C.POINTER(C.c_void_p)],
         "dgpt_ipc_close": [vp, i64],
@@ -101,6 +106,10 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = i32
         fn.argtypes = args
+    lib.dgpt_decode_persistent_max_batch.restype = i32
+    lib.dgpt_decode_persistent_max_batch.argtypes = []
+    lib.dgpt_decode_persistent_scratch_floats.restype = i64
+    lib.dgpt_decode_persistent_scratch_floats.argtypes = [i32, i32, i32, i32, i32]
     lib.dgpt_attn_bwd_scratch_bytes.restype = i64
     lib.dgpt_attn_bwd_scratch_bytes.argtypes = [C.POINTER(AttnArgs)]
 

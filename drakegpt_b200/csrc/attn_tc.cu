@@ -293,7 +293,7 @@ struct FwdSched {
 };
 
 __global__ void __launch_bounds__(kFwd2Threads, 1)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q32, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, AttnTcP p, FwdSched sc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -333,7 +333,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   };
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_q32);
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
     for (int g = 0; g < 2; ++g) {
@@ -367,7 +367,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(&qk_empty[g], (k & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&qk_full[g], 16384 * (1 + nkv));
-        tma_load_2d(q_s, &map_q, &qk_full[g], h * HD, row0 + qt * QT);
+        // warpgroup 1 takes its query tile with the four 32-row blocks in REVERSE order: causal rows near the end of
+        // the tile see more keys, and a row block is pinned to the sub-partition of its TMEM lane quadrant, so
+        // sub-partition q then serves block q of warpgroup 0's item and block 3 - q of warpgroup 1's (equal load)
+        for (int qb = 0; qb < 4; ++qb)
+          tma_load_2d(q_s + qb * 4096, &map_q32, &qk_full[g], h * HD, row0 + qt * QT + (g ? 3 - qb : qb) * 32);
         for (int j = 0; j < nkv; ++j) tma_load_2d(q_s + 16384 * (1 + j), &map_k, &qk_full[g], h * HD, row0 + j * QT);
       }
       __syncwarp();
@@ -440,7 +444,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // ---------------------------- softmax + output: one thread per query row ----------
     const int g = warp >> 2;     // warpgroup = TMEM slot = shared-memory stage
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    const int rblk = g ? 3 - quad : quad;  // which 32-row block of the query tile sits in this warp's TMEM lanes
+    const int row = rblk * 32 + lane;
     const uint32_t taddr = tmem + (uint32_t)(g * 256) + ((uint32_t)(quad * 32) << 16);
     uint64_t seed = p.seed;
     if (p.thr && p.seed_dev) seed += *p.seed_dev;
@@ -459,7 +464,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_after();
       // tcgen05.ld is warp-collective: loop bounds must be warp-uniform, so the LAST row of this warp decides which
       // 32-column chunks are fully masked; chunks entirely left of the diagonal need no per-element causal test
-      const int qg_max = qt * QT + quad * 32 + 31, qg_min = qt * QT + quad * 32;
+      const int qg_max = qt * QT + rblk * 32 + 31, qg_min = qt * QT + rblk * 32;
       float mx = -INFINITY;
       for (int cc = 0; cc < ncols && cc <= qg_max; cc += 32) {
         uint32_t r[32];
@@ -949,6 +954,7 @@ int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
   if ((rc = make_tmap_bf16_2d(&mv, a->v, cols, rows, a->v_rs, 64))) return rc;
   AttnTcP p = make_tc_params(a);
   if (attn_fwd_variant() != 1) {
+    if ((rc = make_tmap_bf16_2d(&mq, a->q, cols, rows, a->q_rs, 32))) return rc;  // 32-row blocks (see the producer)
     static bool attr2 = false;
     if (!attr2) {
       cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem);

@@ -39,6 +39,7 @@ struct TcParams {
   int vec_ok;      // epilogue operands (bias / residual) allow the vector fast path
   int store_mode;  // StoreMode for D
   int cta_group;   // 1, or 2 = CTA pairs (cluster of 2) sharing each MMA
+  int coalesced;   // output blocks leave by coalesced st.global from the staging tile instead of TMA stores
   int role_hi;     // warp-role placement: 1 = producer / MMA issuer take the two HIGHEST warp ids (8, 9)
   int debug;       // DGPT_GEMM_DEBUG bits (timing experiments only): 1 = epilogue skipped, 2 = no TMA loads / MMAs,
                    // 4 = epilogue without the output stores, 8 = epilogue without the math, 16 / 32 = B operand loaded on
@@ -66,7 +67,10 @@ struct TcCfg {
   // 4 KB staging buffers per epilogue warp: 2, or (residual epilogues) the warp's fp32 blocks of one tile
   // (RESBUFS = 2) or of two tiles (RESBUFS = 4)
   static constexpr int kResBlocks = BN / 2 / 32;
-  static constexpr int kStagingBufs = RESBUFS ? (RESBUFS / 2) * kResBlocks : 2;
+#ifndef DGPT_STAGING_BUFS
+#define DGPT_STAGING_BUFS 2
+#endif
+  static constexpr int kStagingBufs = RESBUFS ? (RESBUFS / 2) * kResBlocks : DGPT_STAGING_BUFS;
   static constexpr int kStagingBytes = 8 * kStagingBufs * 4096;
   static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
   static constexpr int kBarBytes = 512;
@@ -281,6 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   pdl_wait();
 
   // tile walk: with CG = 2 the pair handles pair-tiles (256 rows) and CTA rank r takes rows [128 r, 128 r + 128)
+  const bool prof = p.probe != nullptr && blockIdx.x == 0;  // DGPT_CLOCK_PROBE: where the roles of CTA 0 wait
   const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int tiles_mn = (p.m_tiles / CG) * p.n_tiles;
   const int total_tiles = tiles_mn * p.split_k;
@@ -291,12 +296,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // the whole warp walks the loop (uniform control flow); one elected lane issues
     int s = 0;
     uint32_t ph = 0;
+    long long pr_wait = 0;
+    const long long pr_t0 = prof ? clock64() : 0;
     for (int t = t_first; t < total_tiles; t += t_step) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
       const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
+        const long long tw0 = prof ? clock64() : 0;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (prof) pr_wait += clock64() - tw0;
         uint8_t* sa = stage_base + (size_t)s * Cfg::kStageBytes;
         uint8_t* sb = sa + kABytes;
         const int k0 = kb * TBK;
@@ -358,6 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
+    if (prof && lane == 0) { p.probe[24] = (unsigned long long)(clock64() - pr_t0); p.probe[25] = (unsigned long long)pr_wait; }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer -----------------------------
     if (crank == 0) {  // with CG = 2 only the pair's leader issues MMAs; whole warp loops, one elected lane issues
@@ -365,15 +375,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
+      long long mm_wacc = 0, mm_wfull = 0;
+      const long long mm_t0 = prof ? clock64() : 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         const int ks = t / tiles_mn;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const bool cs_tile = CS && ((t - ks * tiles_mn) % p.n_tiles) == 0;  // column sums: once per row tile
+        const long long ta0 = prof ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        if (prof) mm_wacc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
+          const long long tf0 = prof ? clock64() : 0;
           mbar_wait(&full_bar[s], ph);
+          if (prof) mm_wfull += clock64() - tf0;
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
@@ -408,6 +424,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+      if (prof && lane == 0) {
+        p.probe[8] = (unsigned long long)(clock64() - mm_t0);
+        p.probe[9] = (unsigned long long)mm_wacc;
+        p.probe[10] = (unsigned long long)mm_wfull;
       }
     }
   } else {
@@ -463,6 +484,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     };
     if (kRes && lane == 0 && t_first < total_tiles && !(p.debug & 1)) res_prefetch(t_first, 0);
 
+    long long ep_wfull = 0, ep_wread = 0, ep_wres = 0;
+    const long long ep_t0 = prof ? clock64() : 0;
     for (int t = t_first; t < total_tiles; t += t_step, ++it) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
       const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
@@ -486,8 +509,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mk_in[w] = (active && m < p.M && 32 * w < ncols && nbeg + 32 * w < p.N) ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + m) : 0u;
       }
       const int par = kResAhead ? (it & 1) : 0;
+      const long long tr0 = prof ? clock64() : 0;
       if (kRes && !(p.debug & 1)) mbar_wait(&my_res_bar[par], (uint32_t)(kResAhead ? (it >> 1) : it) & 1u);
+      const long long tr1 = prof ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_ph);
+      if (prof) { ep_wres += tr1 - tr0; ep_wfull += clock64() - tr1; }
       tc_fence_after();
       const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col_beg);
 #pragma unroll 1
@@ -502,9 +528,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r0[32], r1[32];
         tmem_ld32(row_addr + b * cpb, r0);
         if (cpb == 64) tmem_ld32(row_addr + b * cpb + 32, r1);
-        if (!kRes && mode != kStoreDirect) {
-          if (lane == 0) bulk_wait_read<kBufs - 1>();  // the store that last used this buffer has drained it
+        // coalesced mode (full blocks of plain stores): the block is read back from the staging tile by the warp
+        // itself and leaves through the LSU, 4 rows x 128 B per instruction -- no bulk group to wait for, and the
+        // stores do not queue behind the operand loads in the TMA unit
+        const bool coal = !kRes && p.coalesced && mode == kStoreTma && n + cpb <= p.N;
+        if (!kRes && mode != kStoreDirect && !coal) {
+          const long long tb0 = prof ? clock64() : 0;
+          if (lane == 0) {
+            if (p.coalesced) bulk_wait_read<0>();
+            else bulk_wait_read<kBufs - 1>();  // the store that last used this buffer has drained it
+          }
           __syncwarp();
+          if (prof) ep_wread += clock64() - tb0;
         }
         tmem_ld_wait();
         const bool fast = kFast && p.vec_ok && mode != kStoreDirect && n + cpb <= p.N;
@@ -546,6 +581,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else {
           stage_row_f32(tile, lane, r0);
         }
+        if (coal) {
+          __syncwarp();
+          const int esz = out_bf16 ? 2 : 4;
+          char* dbase = reinterpret_cast<char*>(ep.D) + ((int64_t)mrow0 * ep.ldd + n) * esz;
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3), chunk = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4));
+              if (mrow0 + row < p.M) *reinterpret_cast<uint4*>(dbase + (int64_t)row * ep.ldd * esz + chunk * 16) = v;
+            }
+          }
+          __syncwarp();  // the tile may be rewritten
+          nbuf = (nbuf + 1 == kBufs) ? 0 : nbuf + 1;
+          continue;
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -553,7 +604,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else if (mode == kStoreTmaAdd) tma_reduce_add_2d(&map_d, tile, n, mrow0);
           else tma_store_2d(&map_d, tile, n, mrow0);
           bulk_commit();
+          if (!kRes && p.coalesced) bulk_wait_read<0>();  // (ragged block in coalesced mode: free the tile at once)
         }
+        if (!kRes && p.coalesced) __syncwarp();
         if (!kRes) nbuf = (nbuf + 1 == kBufs) ? 0 : nbuf + 1;
       }
       if (CS && n0 == 0 && half == 0 && mrow0 < p.M) {
@@ -583,7 +636,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (prof && ew == 0 && lane == 0) {
+      p.probe[16] = (unsigned long long)(clock64() - ep_t0);
+      p.probe[17] = (unsigned long long)ep_wfull;
+      p.probe[18] = (unsigned long long)ep_wread;
+      p.probe[19] = (unsigned long long)ep_wres;
+    }
+    const long long td0 = prof ? clock64() : 0;
     if (lane == 0) bulk_wait<0>();  // all output tiles have landed before the CTA retires
+    if (prof && ew == 0 && lane == 0) p.probe[20] = (unsigned long long)(clock64() - td0);
   }
 
   tc_fence_before();
@@ -764,6 +825,9 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     static int role_hi = -1;
     if (role_hi < 0) { const char* e = getenv("DGPT_GEMM_ROLE_HI"); role_hi = e ? atoi(e) : 0; }
     p.role_hi = role_hi;
+    static int coal = -1;
+    if (coal < 0) { const char* e = getenv("DGPT_GEMM_STORE"); coal = (e && e[0] == 'c') ? 1 : 0; }
+    p.coalesced = coal;
   }
   p.mask_out = a->relu_mask_out;
   p.mask_in = a->relu_mask_in;

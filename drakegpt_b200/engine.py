@@ -476,7 +476,10 @@ class Runner:
         for li, L in enumerate(sp["layers"]):
             NH, H = L["NH"], L["H"]
             D = NH * H
-            cache = caches[li]  # [ctx, B, 3D] time-major: row t is a contiguous (B, 3D) GEMM output
+            # [B, ctx, 3D] sequence-major: the packed q | k | v of position t is written by the QKV GEMM through a
+            # strided output view (row pitch ctx * 3D), and the keys / values of one sequence sit next to each other,
+            # 3D elements apart, so the decode attention streams whole DRAM pages instead of one 128-byte row per page
+            cache = caches[li]
             if L["ln1"] is not None:
                 a = self.buf("d.xn1", (Bn, C))
                 ops.raw_ln_fwd(x, self.f(L["ln1"][0]), self.f(L["ln1"][1]), a, self.buf("d.mean", (Bn,), torch.float32),
@@ -485,11 +488,14 @@ class Runner:
                 a = ops.raw_dropout_scale(x, self.buf("d.xn1", (Bn, C)))
             else:
                 a = x
-            self._gemm(a, self.w(L["qkv"]).view(3 * D, C), cache[t])
-            q = cache[t].view(Bn, 1, 3 * D)[:, :, :D]
-            kv = cache[: t + 1].permute(1, 0, 2)  # (B, t+1, 3D) view
+            self._gemm(a, self.w(L["qkv"]).view(3 * D, C), cache[:, t])
+            q = cache[:, t:t + 1, :D]
+            kv = cache[:, : t + 1]  # (B, t+1, 3D) view
             att = self.buf("d.att", (Bn, D))
-            ops.raw_attn_fwd(q, kv[:, :, D:2 * D], kv[:, :, 2 * D:], att.view(Bn, 1, D), None, NH, H, H ** -0.5)
+            if ops.decode_attn_supported(q, kv, H):  # tensor mode, head size 64: the KV-streaming decode kernel
+                ops.raw_decode_attn(q, kv[:, :, D:2 * D], kv[:, :, 2 * D:], att.view(Bn, 1, D), NH, H, H ** -0.5)
+            else:
+                ops.raw_attn_fwd(q, kv[:, :, D:2 * D], kv[:, :, 2 * D:], att.view(Bn, 1, D), None, NH, H, H ** -0.5)
             if L["proj"] is not None:
                 x1 = self.buf("d.x1", (Bn, C), torch.float32)
                 self._gemm(att, self.w(L["proj"][0]), x1, bias=self.f(L["proj"][1]),
@@ -518,14 +524,61 @@ class Runner:
             x = out
         return x
 
+    def _persistent_decode_ok(self, Bn):
+        """The one-launch persistent decoder covers the TransformerLM block structure in tensor mode, head size 64,
+        context <= 256, up to 8 sequences per 16-CTA cluster (72 on a 148-SM B200); DGPT_DECODE_PERSISTENT=0 turns it
+        off for A/B runs."""
+        import os
+        from . import _lib
+        sp = self.spec
+        if self.mode != "bf16" or os.environ.get("DGPT_DECODE_PERSISTENT", "1") == "0":
+            return False
+        if not (1 <= Bn <= int(_lib.lib().dgpt_decode_persistent_max_batch())):
+            return False
+        if sp["ctx"] is None or sp["ctx"] > 256 or not (1 <= len(sp["layers"]) <= 8):
+            return False
+        C = self.f(sp["tok"]).shape[1]
+        for L in sp["layers"]:
+            if (L["H"] != 64 or L["ln1"] is None or L["ln2"] is None or L["proj"] is None or not L["residual"]
+                    or L["ffn"] is None or L["ffn"][0] != "mlp" or L["NH"] * L["H"] != C):
+                return False
+        return C % 8 == 0
+
+    def _decode_persistent(self, seqw, caches, Bn, t_begin, t_end, t_sample, greedy, seed_dev):
+        import ctypes as C_
+        from . import _lib
+        sp = self.spec
+        tok = self.f(sp["tok"])
+        V, C = tok.shape
+        L0 = sp["layers"][0]
+        NH, H = L0["NH"], L0["H"]
+        F = self.f(L0["ffn"][1]).shape[0]
+        lib = _lib.lib()
+        nfl = int(lib.dgpt_decode_persistent_scratch_floats(Bn, C, NH, F, V))
+        scratch = self.buf("d.pscratch", (nfl,), torch.float32)
+        ptrs = (C_.c_void_p * (12 * len(sp["layers"])))()
+        for li, L in enumerate(sp["layers"]):
+            ts = [self.w(L["qkv"]), self.w(L["proj"][0]), self.w(L["ffn"][1]), self.w(L["ffn"][3]),
+                  self.f(L["ln1"][0]), self.f(L["ln1"][1]), self.f(L["ln2"][0]), self.f(L["ln2"][1]),
+                  self.f(L["proj"][1]), self.f(L["ffn"][2]), self.f(L["ffn"][4]), caches[li]]
+            for j, t in enumerate(ts):
+                ptrs[12 * li + j] = t.data_ptr()
+        _lib.check(lib.dgpt_decode_persistent(ptrs, len(sp["layers"]), tok.data_ptr(), self.f(sp["pos"]).data_ptr(),
+                                              self.w(sp["lm"][0]).data_ptr(), self.f(sp["lm"][1]).data_ptr(),
+                                              seqw.data_ptr(), scratch.data_ptr(), Bn, C, NH, H, F, V, sp["ctx"],
+                                              int(t_begin), int(t_end), int(t_sample), int(bool(greedy)), 0,
+                                              seed_dev.data_ptr(), 0, ops._stream()), "dgpt_decode_persistent")
+
     @torch.no_grad()
     def generate(self, idx, max_new_tokens, greedy=False, seed=None, use_graphs=None):
         """(B,t0) int64 -> (B,t0+N) int64.  Sampling (softmax -> multinomial, or argmax) runs on the device.
 
-        While the window has not slid (t < context_length) every position is one KV-cached decode step;
-        with ``use_graphs`` (default: tensor mode) each (batch, position) step is captured once in a CUDA
-        graph -- the sequence buffer, KV caches and sampling seed live in device memory -- and later calls
-        replay it, which removes the ~50 host-side kernel launches per token.
+        While the window has not slid (t < context_length) every position is one KV-cached decode step.
+        Tensor mode, up to 8 sequences: ONE cooperative launch of the persistent decoder (``dgpt_decode_persistent``)
+        walks all in-window positions.  Larger batches: per-position kernel sequences (tcgen05 GEMMs on the M = batch
+        rows + the KV-streaming attention kernel), each (batch, position) step captured once in a CUDA graph with
+        ``use_graphs`` (default: tensor mode) -- the sequence buffer, KV caches and sampling seed live in device memory.
+        After the slide every token is a full-window recompute (reference semantics, src/model.py:625).
         """
         self._reattach()
         self.flat.refresh_shadow()
@@ -553,11 +606,19 @@ class Runner:
         seq[:t0].copy_(idx.t())
         if seq is not seqw:
             seqw[:min(t0, ctx + 1)].copy_(seq[:min(t0, ctx + 1)])
-        caches = [self.buf(f"d.cache{li}", (ctx, Bn, 3 * L["NH"] * L["H"])) for li, L in enumerate(sp["layers"])]
+        caches = [self.buf(f"d.cache{li}", (Bn, ctx, 3 * L["NH"] * L["H"])) for li, L in enumerate(sp["layers"])]
         logits = self.buf("d.logits", (Bn, V), torch.float32)
         sample_seed = self.buf("d.seed", (1,), torch.int64)
         sample_seed.fill_(seed)
         graphs = self.__dict__.setdefault("_decode_graphs", {})
+        n_in = min(total - 1, ctx)  # positions decoded inside the window
+        if self._persistent_decode_ok(Bn) and n_in > 0:
+            # small / medium batch: ONE launch (a thread-block cluster per <= 8 sequences) walks every in-window position (all layers, KV append, attention,
+            # LM head, sampling) -- no per-token launches at all
+            self._decode_persistent(seqw, caches, Bn, 0, n_in, t0 - 1, greedy, sample_seed)
+            n_done = n_in
+        else:
+            n_done = 0
 
         def step_kernels(t, sampling, greedy_flag):
             x = self._decode_token(seqw[t], t, caches)
@@ -566,7 +627,7 @@ class Runner:
                 self._gemm(xin, self.w(sp["lm"][0]), logits, bias=self.f(sp["lm"][1]))
                 ops.raw_sample(logits, seqw[t + 1], 0, greedy_flag, 0, t, seed_dev=sample_seed)
 
-        for t in range(min(total - 1, ctx)):
+        for t in range(n_done, n_in):
             sampling = t >= t0 - 1
             if not use_graphs:
                 step_kernels(t, sampling, greedy)

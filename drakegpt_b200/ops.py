@@ -159,6 +159,21 @@ def raw_attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, scratch, NH, H, scale, dropou
     check(_lib.lib().dgpt_attn_bwd(C.byref(a), _stream()), "dgpt_attn_bwd")
 
 
+def decode_attn_supported(q, k, H):
+    """The bf16 KV-cache attention kernel covers head size 64 and up to 256 cached positions."""
+    return q.dtype == torch.bfloat16 and H == 64 and q.shape[1] == 1 and 1 <= k.shape[1] <= 256
+
+
+def raw_decode_attn(q, k, v, o, NH, H, scale):
+    """One new query per (sequence, head) against the cached keys / values; see dgpt_decode_attn.
+    q, o: [B, 1, >= NH*H]; k, v: [B, nk, >= NH*H] views (any batch / time strides, unit inner stride)."""
+    _need_cuda(q, k, v, o)
+    check(_lib.lib().dgpt_decode_attn(_p(q), _p(k), _p(v), _p(o), q.stride(0), k.stride(0), k.stride(1), v.stride(0),
+                                      v.stride(1), o.stride(0), q.shape[0], NH, H, k.shape[1], float(scale), _stream()),
+          "dgpt_decode_attn")
+    return o
+
+
 def raw_embed_fwd(idx, tok, pos, x, pos_offset=0):
     _need_cuda(idx, tok, x)
     B, T = idx.shape

@@ -301,6 +301,43 @@ int dgpt_counter_add(uint64_t* ctr, uint64_t delta, void* stream);
 int dgpt_sample(const float* logits, int ld, int64_t* seq, int64_t seq_ld, int pos, int B, int V,
                 int greedy, uint64_t seed, const uint64_t* seed_dev, uint32_t step, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * KV-cached generation (tensor mode, head size 64, context <= 256) -- the
+ * reference's generate loop, src/model.py:611-636, while the window has not slid.
+ *
+ * dgpt_decode_attn: ONE new query per (sequence, head) against nk cached
+ *   keys / values (bf16): element (b, j, h, d) of k at k + b*k_bs + j*k_rs +
+ *   h*64 + d (same for v); q / o: (b, h, d) at base + b*bs + h*64 + d.
+ *   One warp per (b, h), lanes over keys, 16-byte loads: built to stream the
+ *   KV cache at HBM speed for the large-batch end of the generation sweep.
+ *
+ * dgpt_decode_persistent: ONE launch for all positions t in [t0, t1) of up to
+ *   dgpt_decode_persistent_max_batch() sequences: embedding, per layer
+ *   LayerNorm + packed QKV matrix-vector product + KV append, attention,
+ *   projection + residual, LayerNorm + FFN (+ReLU) + residual, then the LM head
+ *   (ln_f is not applied, src/model.py:598-599) and the next token -- argmax
+ *   (greedy != 0) or the same inverse-CDF / Philox stream as dgpt_sample
+ *   (step = t) -- written to seq[(t+1)*B + b] for t >= t_sample.
+ *   One thread-block CLUSTER (16 CTAs; `cluster` = 4 / 8 / 16, 0 = default) per
+ *   group of <= 8 sequences, hardware cluster barriers between the phases, the
+ *   weight rows of a phase prefetched into registers before the barrier it
+ *   waits on; weights (bf16 shadows) stay L2-resident across tokens.
+ *   layers: HOST array of nl x 12 device pointers per layer: wqkv [3D,C],
+ *     wproj [C,D], w1 [F,C], w2 [C,F] (bf16), ln1 gamma/beta, ln2 gamma/beta,
+ *     proj bias, b1, b2 (fp32), KV cache [B, ctx, 3D] (bf16, sequence-major).
+ *   scratch: dgpt_decode_persistent_scratch_floats() floats.
+ * ------------------------------------------------------------------------- */
+int dgpt_decode_attn(const void* q, const void* k, const void* v, void* o, int64_t q_bs, int64_t k_bs,
+                     int64_t k_rs, int64_t v_bs, int64_t v_rs, int64_t o_bs, int B, int NH, int H,
+                     int nk, float scale, void* stream);
+int64_t dgpt_decode_persistent_scratch_floats(int B, int C, int NH, int F, int V);
+int dgpt_decode_persistent_max_batch(void);
+int dgpt_decode_persistent(const void* const* layers, int nl, const float* tok, const float* pos,
+                           const void* wlm, const float* blm, int64_t* seq, float* scratch, int B,
+                           int C, int NH, int H, int F, int V, int ctx, int t0, int t1, int t_sample,
+                           int greedy, uint64_t seed, const uint64_t* seed_dev, int cluster,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif
