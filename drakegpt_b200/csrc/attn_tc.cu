@@ -269,7 +269,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ===========================================================================
-// forward, persistent form (default): one CTA per SM walks a statically balanced list of (batch, head, query
+// forward, persistent form (DGPT_ATTN_FWD=2, the default): one CTA per SM walks a statically balanced list of (batch, head, query
 // tile) items with TWO items in flight, so that the serial phases of one item (TMA latency, S MMAs, softmax, P V,
 // output) are filled with the other item's work instead of idling the SM:
 //   warp 8   TMA producer: Q / K and V tiles of item n into stage n & 1 (the Q / K stage is released as soon as the
@@ -556,6 +556,293 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q32, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+  clock_probe_end(sc.probe);
+}
+
+// ===========================================================================
+// forward, persistent form with TWO softmax threads per query row (DGPT_ATTN_FWD=3; measured slower with dropout).  Same pipeline as attn_fwd_tc2_kernel
+// (two items in flight, TMA producer and tcgen05 issuer on the highest warp ids), but a warpgroup is 8 warps: thread A
+// of a row (warps 0-3 of the group) owns the first half of the key columns, thread B (warps 4-7, same TMEM lane
+// quadrant) the second half, so the serial exp2 / dropout / pack chain of an item is half as long and 16 softmax
+// warps instead of 8 hide each other's latencies.  Row max and row sum are exchanged through shared memory (two
+// named barriers per item).  P (bf16) of each half overlays the S columns its own thread has consumed:
+//     keys [0, n/2) -> columns [0, n/4),  keys [n/2, n) -> columns [n/2, 3n/4);  O above both (n = 128 or 256 keys).
+// ===========================================================================
+static constexpr int kFwd3Threads = 576;  // 16 softmax warps, TMA producer (warp 16), tcgen05 issuer (warp 17)
+static constexpr int kFwd3Smem = 2 * kFwd2QK + 2 * 32768 + 4096 + 256 + 1024;
+
+__global__ void __launch_bounds__(kFwd3Threads, 1)
+attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_q32, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, AttnTcP p, FwdSched sc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQK = smem;                    // [2][Q | K0 | K1]
+  uint8_t* sV = smem + 2 * kFwd2QK;       // [2][4 x 8 KB]
+  float* xch = reinterpret_cast<float*>(sV + 2 * 32768);  // [2 groups][max: 2 x 128 | sum: 2 x 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * 32768 + 4096);
+  uint64_t *qk_full = bars, *qk_empty = bars + 2, *v_full = bars + 4, *v_empty = bars + 6, *s_full = bars + 8,
+           *p_full = bars + 10, *o_full = bars + 12, *slot_free = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  clock_probe_begin(sc.probe);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = p.T / QT;
+
+  // ---- this CTA's item list (see attn_fwd_tc2_kernel) ----
+  const int G = gridDim.x, c = blockIdx.x;
+  const int hq = sc.nheavy / G, hr = sc.nheavy % G;
+  const int nh_c = hq + (c < hr ? 1 : 0);
+  const int U = (kWHeavy * sc.nheavy + kWLight * sc.nlight + G - 1) / G;
+  const int cap_hi = max(0, (U - kWHeavy * (hq + 1)) / kWLight), cap_lo = max(0, (U - kWHeavy * hq) / kWLight);
+  const int cap_total = hr * cap_hi + (G - hr) * cap_lo;
+  const int l_start = c < hr ? c * cap_hi : hr * cap_hi + (c - hr) * cap_lo;
+  const int l0 = min(sc.nlight, l_start), l1 = min(sc.nlight, l_start + (c < hr ? cap_hi : cap_lo));
+  const int n_extra = cap_total < sc.nlight ? (sc.nlight - cap_total - c + G - 1) / G : 0;
+  const int n_items = nh_c + (l1 - l0) + max(0, n_extra);
+  auto item = [&](int n, int& bh, int& qt) {
+    if (n < nh_c) {
+      bh = c + n * G; qt = ntile - 1;
+    } else {
+      const int m = n - nh_c;
+      bh = m < l1 - l0 ? l0 + m : cap_total + c + (m - (l1 - l0)) * G;
+      qt = 0;
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_q32);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&qk_full[g], 1);
+      mbar_init(&qk_empty[g], 1);
+      mbar_init(&v_full[g], 1);
+      mbar_init(&v_empty[g], 1);
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 8);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&slot_free[g], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_grid_sync();  // prologue done (shared memory / TMEM only); global memory from here on
+
+  if (warp == 16) {
+    // ------------------------------ TMA producer ---------------------------
+    for (int n = 0; n < n_items; ++n) {
+      const int g = n & 1, k = n >> 1;
+      int bh, qt;
+      item(n, bh, qt);
+      const int nkv = qt + 1, b = bh / p.NH, h = bh % p.NH, row0 = b * p.T;
+      uint8_t* q_s = sQK + g * kFwd2QK;
+      uint8_t* v_s = sV + g * 32768;
+      mbar_wait(&qk_empty[g], (k & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&qk_full[g], 16384 * (1 + nkv));
+        for (int qb = 0; qb < 4; ++qb)  // group 1 takes its query row blocks in reverse order (sub-partition balance)
+          tma_load_2d(q_s + qb * 4096, &map_q32, &qk_full[g], h * HD, row0 + qt * QT + (g ? 3 - qb : qb) * 32);
+        for (int j = 0; j < nkv; ++j) tma_load_2d(q_s + 16384 * (1 + j), &map_k, &qk_full[g], h * HD, row0 + j * QT);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[g], (k & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[g], 16384 * nkv);
+        for (int kb = 0; kb < 2 * nkv; ++kb) tma_load_2d(v_s + kb * 8192, &map_v, &v_full[g], h * HD, row0 + kb * 64);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 17) {
+    // ------------------------------ MMA issuer -----------------------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+    int next_s = 0, next_pv = 0;
+    while (next_pv < n_items) {
+      bool progressed = false;
+      if (next_s < n_items) {
+        const int g = next_s & 1, k = next_s >> 1;
+        if (mbar_test(&qk_full[g], k & 1) && mbar_test(&slot_free[g], (k & 1) ^ 1)) {
+          tc_fence_after();
+          int bh, qt;
+          item(next_s, bh, qt);
+          const int nkv = qt + 1;
+          const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQK + g * kFwd2QK), 16, 1024);
+          const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sQK + g * kFwd2QK + 16384), 16, 1024);
+          if (elect_one()) {
+            for (int j = 0; j < nkv; ++j) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_bf16(tmem + g * 256 + j * 128, dq0 + (uint64_t)(kk * 2), dk0 + (uint64_t)(j * 1024 + kk * 2), idesc_s, kk > 0);
+            }
+            tc_commit(&s_full[g]);
+            tc_commit(&qk_empty[g]);
+          }
+          __syncwarp();
+          ++next_s;
+          progressed = true;
+        }
+      }
+      if (next_pv < next_s) {
+        const int g = next_pv & 1, k = next_pv >> 1;
+        if (mbar_test(&p_full[g], k & 1) && mbar_test(&v_full[g], k & 1)) {
+          tc_fence_after();
+          int bh, qt;
+          item(next_pv, bh, qt);
+          const int nkv = qt + 1;
+          const uint32_t ocol = nkv == 2 ? 192u : 128u;
+          const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV + g * 32768), 8192, 1024);
+          if (elect_one()) {
+            for (int kb = 0; kb < 2 * nkv; ++kb) {
+              // P of the 64-key block kb: first half of the keys at columns [0, ..), second half at [nkv * 64, ..)
+              const uint32_t pcol = kb < nkv ? (uint32_t)(kb * 32) : (uint32_t)(nkv * 64 + (kb - nkv) * 32);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_bf16_ts(tmem + g * 256 + ocol, tmem + g * 256 + pcol + kk * 8, dv0 + (uint64_t)(kb * 512 + kk * 128), idesc_o,
+                               (kb | kk) > 0);
+            }
+            tc_commit(&o_full[g]);
+            tc_commit(&v_empty[g]);
+          }
+          __syncwarp();
+          ++next_pv;
+          progressed = true;
+        }
+      }
+      if (!progressed) __nanosleep(32);
+    }
+  } else {
+    // ---------------------------- softmax + output: two threads per query row ----------
+    const int g = warp >> 3;            // warpgroup = TMEM slot = shared-memory stage
+    const int quad = warp & 3;
+    const int hc = (warp >> 2) & 1;     // 0: first half of the key columns, 1: second half
+    const int rblk = g ? 3 - quad : quad;
+    const int row = rblk * 32 + lane;
+    const uint32_t taddr = tmem + (uint32_t)(g * 256) + ((uint32_t)(quad * 32) << 16);
+    float* xmax = xch + g * 512;        // [2][128]
+    float* xsum = xmax + 256;           // [2][128]
+    uint64_t seed = p.seed;
+    if (p.thr && p.seed_dev) seed += *p.seed_dev;
+    const float sc2 = p.scale * kLog2e;
+    for (int n = g; n < n_items; n += 2) {
+      const int k = n >> 1;
+      int bh, qt;
+      item(n, bh, qt);
+      const int nkv = qt + 1, b = bh / p.NH, h = bh % p.NH, row0 = b * p.T;
+      const int qg = qt * QT + row;             // query position inside the sequence
+      const int hcols = nkv * (QT / 2);         // key columns per thread: 64 or 128
+      const int c_beg = hc * hcols, c_end = c_beg + hcols;
+      const uint32_t pbase = hc ? (uint32_t)hcols : 0u;  // where this thread's P goes (32-bit TMEM columns)
+      const uint32_t ocol = nkv == 2 ? 192u : 128u;
+#define FTS3(i) do { if (sc.probe && blockIdx.x == 0 && warp == 0 && lane == 0 && k < 3) sc.probe[4 + k * 8 + (i)] = (unsigned long long)clock64(); } while (0)
+      FTS3(0);
+      mbar_wait(&s_full[g], k & 1);
+      FTS3(1);
+      tc_fence_after();
+      const int qg_max = qt * QT + rblk * 32 + 31, qg_min = qt * QT + rblk * 32;  // (warp-uniform loop bounds)
+      float mx = -INFINITY;
+      for (int cc = c_beg; cc < c_end && cc <= qg_max; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + cc, r);
+        tmem_ld_wait();
+        if (cc + 31 <= qg_min) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc + j <= qg) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      }
+      xmax[hc * 128 + quad * 32 + lane] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+      mx = fmaxf(mx, xmax[(hc ^ 1) * 128 + quad * 32 + lane]);  // (the first half always holds key 0: finite)
+      FTS3(2);
+      const float msc = mx * sc2;
+      float sum = 0.f;
+      const uint64_t base = (((uint64_t)b * p.NH + h) * p.T + qg) * (uint64_t)p.T;
+      DropGroup dg = {0u, 0u};
+      for (int cc = c_beg; cc < c_end; cc += 16) {
+        float e[16];
+        if (cc > qg_max) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e[j] = 0.f;
+        } else {
+          uint32_t r[16];
+          tmem_ld16(taddr + cc, r);
+          tmem_ld_wait();
+          if (cc + 15 <= qg_min) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = exp2f(__uint_as_float(r[j]) * sc2 - msc);
+              sum += v;
+              e[j] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = (cc + j <= qg) ? exp2f(__uint_as_float(r[j]) * sc2 - msc) : 0.f;
+              sum += v;
+              e[j] = v;
+            }
+          }
+          if (p.thr) {  // 32 keys are one mask group (T % 32 == 0): one hash per two 16-key steps
+            if ((cc & 16) == 0) dg = dropout_group(seed, p.site, (base + cc) >> 5);
+            const uint32_t e0 = (uint32_t)(cc & 16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (dropout_word(dg, e0 + j) < p.thr) e[j] = 0.f;
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(e[2 * j], e[2 * j + 1]);
+        tmem_st8(taddr + pbase + (uint32_t)((cc - c_beg) >> 1), pk);
+      }
+      xsum[hc * 128 + quad * 32 + lane] = sum;
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+      sum += xsum[(hc ^ 1) * 128 + quad * 32 + lane];
+      if (hc == 0 && p.lse) p.lse[((int64_t)b * p.NH + h) * p.T + qg] = mx * p.scale + logf(sum);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      FTS3(3);
+      // output: each of the two threads of a row converts and stores half of the 64 head dims
+      mbar_wait(&o_full[g], k & 1);
+      FTS3(4);
+      tc_fence_after();
+      const float oscale = p.inv_keep / sum;
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.o) + (int64_t)(row0 + qg) * p.o_rs + h * HD + hc * 32;
+      {
+        uint32_t r[32];
+        tmem_ld32(taddr + ocol + hc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(r[8 * j]) * oscale, __uint_as_float(r[8 * j + 1]) * oscale);
+          w.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * oscale, __uint_as_float(r[8 * j + 3]) * oscale);
+          w.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * oscale, __uint_as_float(r[8 * j + 5]) * oscale);
+          w.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * oscale, __uint_as_float(r[8 * j + 7]) * oscale);
+          *reinterpret_cast<uint4*>(orow + 8 * j) = w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);  // TMEM slot g may take the S of item n + 2
+      FTS3(5);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -938,7 +1225,9 @@ static AttnTcP make_tc_params(const dgpt_attn_args* a) {
   return p;
 }
 
-// DGPT_ATTN_FWD=1 selects the round-1 one-item-per-CTA forward kernel (A/B experiments); default: persistent form
+// DGPT_ATTN_FWD: 1 = the round-1 one-item-per-CTA kernel (26.6 us at the model shape), 2 = persistent, one softmax
+// thread per row (default: 23.2 us with dropout 0.2, 21.3 without), 3 = persistent, two softmax threads per row
+// (20.8 us without dropout but 28.5 us with it: 16 softmax warps saturate the issue slots the mask costs)
 static int attn_fwd_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DGPT_ATTN_FWD"); v = e ? atoi(e) : 2; }
@@ -969,6 +1258,16 @@ int launch_attn_fwd_tc(const dgpt_attn_args* a, cudaStream_t st) {
     int sms = dgpt_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = min(sms, sc.nheavy + sc.nlight);
+    if (attn_fwd_variant() == 3) {
+      static bool attr3 = false;
+      if (!attr3) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem);
+        if (e != cudaSuccess) { set_error("attn_fwd_tc3: smem attribute: %s", cudaGetErrorString(e)); return DGPT_E_LAUNCH; }
+        attr3 = true;
+      }
+      launch_pdl(attn_fwd_tc3_kernel, dim3(grid), dim3(kFwd3Threads), kFwd3Smem, st, mq, mk, mv, p, sc);
+      return check_launch("attn_fwd_tc3");
+    }
     launch_pdl(attn_fwd_tc2_kernel, dim3(grid), dim3(kFwd2Threads), kFwd2Smem, st, mq, mk, mv, p, sc);
     return check_launch("attn_fwd_tc2");
   }

@@ -60,27 +60,34 @@ enum { kEpiBias = 1, kEpiRelu = 2, kEpiAux = 4, kEpiDrop = 8, kEpiRes = 16, kEpi
 // 4 buffers per warp = the next tile's residual is fetched while this tile's stores drain (short-K GEMMs, whose
 // epilogue is the critical path; ring of 3 stages); 2 buffers = fetched once this tile's stores have been read
 // (long-K GEMMs: the epilogue warps have slack, the mainloop wants the 5-stage ring).
-template <int BN, int CG, int RESBUFS, int CS = 0>
+// TM = 128-row sub-tiles per CTA tile (1 or 2).  TM = 2: a 256 x BN tile as two M = 128 MMAs per k-step that share one
+// B stage -- 2/3 of the operand bytes per MMA cycle of a 128 x BN tile (measured: the mainloop of 128-row tiles waits
+// for operands 30-50 % of the time, the SM ingests ~70 B/cycle and a 128 x 256 tile needs 94).  The two accumulators
+// fill TMEM (2 x 256 or 2 x 192 columns), so TM = 2 tiles are single-buffered: the epilogue of a tile does not overlap
+// the mainloop of the next one, which costs little because such GEMMs are launched with <= ~3 tiles per CTA.
+template <int BN, int CG, int RESBUFS, int CS = 0, int TM = 1>
 struct TcCfg {
+  static constexpr int kABytes = TM * TBM * TBK * 2;
   static constexpr int kBBytes = (BN / CG) * TBK * 2;
-  static constexpr int kStageBytes = TBM * TBK * 2 + kBBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
   // 4 KB staging buffers per epilogue warp: 2, or (residual epilogues) the warp's fp32 blocks of one tile
-  // (RESBUFS = 2) or of two tiles (RESBUFS = 4)
+  // (RESBUFS = 2) or of two tiles (RESBUFS = 4); TM = 2 keeps one (the ring needs the room)
   static constexpr int kResBlocks = BN / 2 / 32;
 #ifndef DGPT_STAGING_BUFS
 #define DGPT_STAGING_BUFS 2
 #endif
-  static constexpr int kStagingBufs = RESBUFS ? (RESBUFS / 2) * kResBlocks : DGPT_STAGING_BUFS;
+  static constexpr int kStagingBufs = RESBUFS ? (RESBUFS / 2) * kResBlocks : (TM == 2 ? 1 : DGPT_STAGING_BUFS);
   static constexpr int kStagingBytes = 8 * kStagingBufs * 4096;
   static constexpr int kBiasBytes = 2 * BN * 4;  // bias slice of the tile, double-buffered with the accumulator
   static constexpr int kBarBytes = 512;
   static constexpr int kRing = kSmemMax - kStagingBytes - kBiasBytes - kBarBytes;
   static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
-  // power of two covering both accumulators (+ 2 x 16 column-sum columns with CS)
-  static constexpr int kTmemNeed = 2 * BN + (CS ? 32 : 0);
+  // accumulator buffers: two when they fit the 512 TMEM columns (+ 16 column-sum columns per sub-tile and buffer with CS)
+  static constexpr int kNAcc = (2 * TM * BN + (CS ? 2 * TM * 16 : 0) <= 512) ? 2 : 1;
+  static constexpr int kTmemNeed = kNAcc * TM * BN + (CS ? kNAcc * TM * 16 : 0);
   static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "no TMEM room");
-  static_assert(BN != 192 || CG == 1 || true, "192-column tiles are launched single-CTA only");
+  static_assert(TM == 1 || (CG == 1 && RESBUFS == 0), "256-row CTA tiles: single-CTA MMAs, no TMA-fed residual");
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
   static_assert(kStages >= 3, "shared-memory ring too shallow");
 };
@@ -211,16 +218,19 @@ __device__ __forceinline__ bool kb_nonempty(const TcParams& p, int ks) { return 
 // CS = 1 (wgrad form: A MN-major, plain fp32 epilogue, CG = 1): the column sums of the stored A matrix
 // (= row sums of the logical A: sum_k A[m, k], the bias gradient when A = dY^T) ride on the tensor core as
 // one extra N = 16 MMA per k-step against an all-ones B tile -- no separate pass over dY.
-template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS>
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS, int TM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r, TcParams p) {
   constexpr bool kRes = EPI >= 0 && (EPI & kEpiRes) != 0;
   static_assert(kRes == (RESBUFS != 0), "RESBUFS goes with the residual epilogues");
-  using Cfg = TcCfg<BN, CG, RESBUFS, CS>;
+  using Cfg = TcCfg<BN, CG, RESBUFS, CS, TM>;
   static_assert(!CS || (CG == 1 && EPI == 0), "column sums: single-CTA tiles, plain epilogue");
   constexpr int kStages = Cfg::kStages;
-  constexpr int kABytes = TBM * TBK * 2;
+  constexpr int kABytes = Cfg::kABytes;
+  constexpr int kNAcc = Cfg::kNAcc;
+  constexpr int kTileM = TBM * TM;        // rows of a CTA tile
+  constexpr int kAccCols = TM * BN;       // TMEM columns of one accumulator buffer
   constexpr int kBBytes = Cfg::kBBytes;
   constexpr uint32_t kIdesc = make_idesc_bf16(TBM * CG, BN, A_MN, B_MN);
 
@@ -300,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const long long pr_t0 = prof ? clock64() : 0;
     for (int t = t_first; t < total_tiles; t += t_step) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * kTileM, n0 = (mn % p.n_tiles) * BN;
       const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
         const long long tw0 = prof ? clock64() : 0;
@@ -335,9 +345,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(&full_bar[s], kABytes + (with_b ? kBBytes : 0));
             if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < TBM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
+              for (int c = 0; c < kTileM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
             } else {
-              tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+#pragma unroll
+              for (int mi = 0; mi < TM; ++mi) tma_load_2d(sa + mi * 16384, &map_a, &full_bar[s], k0, m0 + mi * TBM);
             }
             if (with_b) {
               if (B_MN) {
@@ -351,9 +362,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
             if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < TBM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
+              for (int c = 0; c < kTileM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[s], m0 + c * 64, k0);
             } else {
-              tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+#pragma unroll
+              for (int mi = 0; mi < TM; ++mi) tma_load_2d(sa + mi * 16384, &map_a, &full_bar[s], k0, m0 + mi * TBM);
             }
             if (B_MN) {
 #pragma unroll
@@ -385,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         if (prof) mm_wacc += clock64() - ta0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         for (int kb = kb0; kb < kb1 && !(p.debug & 2); ++kb) {
           const long long tf0 = prof ? clock64() : 0;
           mbar_wait(&full_bar[s], ph);
@@ -403,13 +415,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < TBK / UMMA_K; ++k) {
               const uint64_t da = da0 + (uint64_t)(k * (A_MN ? 128 : 2));
               const uint64_t db = db0 + (uint64_t)(k * (B_MN ? 128 : 2));
-              if (CG == 1) tc_mma_bf16(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CG == 2) {
+                tc_mma_bf16_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int mi = 0; mi < TM; ++mi)  // sub-tile mi: 16 KB (1024 descriptor units) further into the A stage
+                  tc_mma_bf16(d_tmem + (uint32_t)(mi * BN), da + (uint64_t)(mi * 1024), db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
               if (CS && cs_tile) {
                 // ones tile: K-major, N = 16 rows as two aliased 8-row groups (SBO = 0), 32 bytes per UMMA_K
                 const uint64_t d1 = make_smem_desc_sw128(smem_u32(bias_s), 16, 0) + (uint64_t)(k * 2);
-                tc_mma_bf16(tmem_base + (uint32_t)(2 * BN + acc * 16), da, d1, make_idesc_bf16(TBM, 16, A_MN, 0),
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int mi = 0; mi < TM; ++mi)
+                  tc_mma_bf16(tmem_base + (uint32_t)(kNAcc * kAccCols + (acc * TM + mi) * 16), da + (uint64_t)(mi * 1024), d1,
+                              make_idesc_bf16(TBM, 16, A_MN, 0), (kb > kb0 || k > 0) ? 1u : 0u);
               }
             }
             if (CG == 1) tc_commit(&empty_bar[s]);  // smem stage is free once these MMAs retire
@@ -423,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else tc_commit_2sm(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        if (++acc == kNAcc) { acc = 0; acc_ph ^= 1; }
       }
       if (prof && lane == 0) {
         p.probe[8] = (unsigned long long)(clock64() - mm_t0);
@@ -473,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr bool kResAhead = RESBUFS == 4;  // a second buffer pair: fetch a whole tile ahead
     auto res_prefetch = [&](int t, int par) {  // lane 0: residual blocks of tile t -> buffers [NBLK par, NBLK par + NBLK)
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * kTileM, n0 = (mn % p.n_tiles) * BN;
       const int nb = n0 + col_beg;
       int cnt = 0;
       for (int b = 0; b < NBLK; ++b) cnt += (nb + b * CPB < p.N) ? 1 : 0;
@@ -488,12 +507,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const long long ep_t0 = prof ? clock64() : 0;
     for (int t = t_first; t < total_tiles; t += t_step, ++it) {
       const int ks = t / tiles_mn, mn = t - ks * tiles_mn;
-      const int m0 = ((mn / p.n_tiles) * CG + crank) * TBM, n0 = (mn % p.n_tiles) * BN;
+      const int m0 = ((mn / p.n_tiles) * CG + crank) * kTileM, n0 = (mn % p.n_tiles) * BN;
       ep.first_split = (ks == 0);
-      const int mrow0 = (p.debug & 1) ? p.M : m0 + quad * 32;  // debug bit 0: skip all epilogue work
-      const int m = mrow0 + lane;
       const int nbeg = n0 + col_beg;
-      const bool active = mrow0 < p.M && nbeg < p.N;
       // stage this tile's bias slice (each warp an eighth) while the accumulator is still being produced
       float* bias_t = bias_s + acc * BN;
       if (kFast && (EPI & kEpiBias)) {
@@ -502,11 +518,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           *reinterpret_cast<float4*>(bias_t + col) = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + col));
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       }
-      uint32_t mk_in[kCols / 32];
+      uint32_t mk_in_all[TM][kCols / 32];  // (fetched before the accumulator wait: the latency hides behind it)
       if (kFast && (EPI & kEpiMaskIn)) {
 #pragma unroll
-        for (int w = 0; w < kCols / 32; ++w)
-          mk_in[w] = (active && m < p.M && 32 * w < ncols && nbeg + 32 * w < p.N) ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + m) : 0u;
+        for (int mi = 0; mi < TM; ++mi) {
+          const int mm = m0 + mi * TBM + quad * 32 + lane;
+#pragma unroll
+          for (int w = 0; w < kCols / 32; ++w)
+            mk_in_all[mi][w] = (!(p.debug & 1) && mm < p.M && 32 * w < ncols && nbeg + 32 * w < p.N)
+                                   ? __ldg(p.mask_in + (size_t)((nbeg >> 5) + w) * p.M + mm) : 0u;
+        }
       }
       const int par = kResAhead ? (it & 1) : 0;
       const long long tr0 = prof ? clock64() : 0;
@@ -515,7 +536,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_ph);
       if (prof) { ep_wres += tr1 - tr0; ep_wfull += clock64() - tr1; }
       tc_fence_after();
-      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col_beg);
+#pragma unroll
+      for (int mi = 0; mi < TM; ++mi) {  // the 128-row sub-tiles of the CTA tile
+      const int mrow0 = (p.debug & 1) ? p.M : m0 + mi * TBM + quad * 32;  // debug bit 0: skip all epilogue work
+      const int m = mrow0 + lane;
+      const bool active = mrow0 < p.M && nbeg < p.N;
+      const uint32_t (&mk_in)[kCols / 32] = mk_in_all[mi];
+      const uint32_t row_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccCols + mi * BN + col_beg);
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
         const int n = nbeg + b * cpb;
@@ -610,10 +637,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (!kRes) nbuf = (nbuf + 1 == kBufs) ? 0 : nbuf + 1;
       }
       if (CS && n0 == 0 && half == 0 && mrow0 < p.M) {
-        const float cs = __uint_as_float(tmem_ld1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * BN + acc * 16)));
+        const float cs = __uint_as_float(tmem_ld1(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                                  (uint32_t)(kNAcc * kAccCols + (acc * TM + mi) * 16)));
         tmem_ld_wait();
         if (m < p.M && kb_nonempty(p, ks)) atomicAdd(p.a_colsum + m, cs);
       }
+      }  // sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -634,7 +663,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == kNAcc) { acc = 0; acc_ph ^= 1; }
     }
     if (prof && ew == 0 && lane == 0) {
       p.probe[16] = (unsigned long long)(clock64() - ep_t0);
@@ -712,11 +741,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t
   return make_tmap_2d(map, base, DGPT_BF16, inner, outer, ld, 64, box_outer);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS = 0>
+template <int BN, int A_MN, int B_MN, int EPI, int OBF, int CG, int RESBUFS, int CS = 0, int TM = 1>
 static int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mr,
                       const TcParams& p, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, CG, RESBUFS, CS>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, OBF, CG, RESBUFS, CS>;
+  using Cfg = TcCfg<BN, CG, RESBUFS, CS, TM>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, OBF, CG, RESBUFS, CS, TM>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -788,7 +817,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     if (cap < 0) { const char* e = getenv("DGPT_GEMM_SMS"); cap = e ? atoi(e) : 0; }
     if (cap > 0 && cap < sms) sms = cap;
   }
-  const int m_tiles = ceil_div(a->M, TBM);
+  int m_tiles = ceil_div(a->M, TBM);
   // 128 x 256 tiles ingest 25 % fewer operand bytes per MMA cycle than 128 x 128; a ragged last column
   // tile (N = 1152 -> 4.5 tiles) costs less than that as soon as N >= 1024 (TMA zero-fills, the store clips)
   int BN = 256;
@@ -799,11 +828,39 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (bn192_env < 0) { const char* e = getenv("DGPT_GEMM_BN192"); bn192_env = e ? atoi(e) : 1; }
   // (measured: ~5 % faster for the dgrad / wgrad GEMMs with >= 8 row tiles; slower with the residual epilogue, whose
   // three staging buffers per warp leave a 3-stage ring, and for small wgrads that would need > 20 K splits)
-  if (bn192_env && BN == 128 && a->N % 192 == 0 && a->N % 256 != 0 && a->N < 1024 && m_tiles >= 8 && !a->residual) BN = 192;
+  // (the bit-mask epilogues are instantiated for 128- / 256-column tiles only)
+  if (bn192_env && BN == 128 && a->N % 192 == 0 && a->N % 256 != 0 && a->N < 1024 && m_tiles >= 8 && !a->residual &&
+      !a->relu_mask_in && !a->relu_mask_out)
+    BN = 192;
   {  // DGPT_GEMM_FORCE_BN=128|256: tile-width experiments (192 only through the rule above)
     static int force = -1;
     if (force < 0) { const char* e = getenv("DGPT_GEMM_FORCE_BN"); force = e ? atoi(e) : 0; }
     if ((force == 128 || force == 256) && !a->a_colsum && !(force == 256 && a->residual)) BN = force;
+  }
+  // 256-row CTA tiles (TM = 2: two M = 128 MMAs per k-step on one B stage, 1/3 fewer operand bytes per MMA cycle) for
+  // the forward / dgrad GEMMs of the model's big activations: plain, bias + ReLU (+ mask) and mask-in epilogues with
+  // bf16 output, no split-K, no residual (the TMA-fed residual path is a 128-row design).  DGPT_GEMM_TM=1 turns it off.
+  static int tm_env = -1;
+  if (tm_env < 0) { const char* e = getenv("DGPT_GEMM_TM"); tm_env = e ? atoi(e) : 0; }
+  int TM = 1;
+  // measured (profiles/r2_gemm_experiments.txt): 256-row tiles are 3 % faster for K >= 1024 (FFN1 / QKV dgrad) and
+  // 10-20 % SLOWER for the K = 384 GEMMs, whose pace is set by the epilogue (single-buffered accumulators serialise it
+  // with the mainloop): default = 256-row tiles only for K >= 1024; DGPT_GEMM_TM=1 never, =2 whenever instantiated
+  if ((tm_env == 2 || (tm_env == 0 && a->K >= 1024)) && !a_mn && a->M >= 1024 && a->d_dtype == DGPT_BF16 && !a->residual && !a->D2 && !a->relu_aux &&
+      a->dropout_p == 0.f && a->split_k <= 1 && !a->accumulate && !a->a_colsum && gemm_cta_group() == 1) {
+    // tile width for 256-row tiles: 192 when it divides N (N = 384, 1152: no ragged column tile), else 256
+    const int bn2 = (a->N % 192 == 0 && a->N % 256 != 0) ? 192 : (a->N >= 256 ? 256 : 0);
+    // only the fast-path epilogues the model uses are instantiated for 256-row tiles (TMA-addressable bf16 output,
+    // vector-aligned bias); everything else keeps 128-row tiles
+    auto al16e = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    const bool fast_ok = al16e(a->D) && ((int64_t)a->ldd * 2) % 16 == 0 && a->N % 4 == 0 && (!a->bias || al16e(a->bias)) &&
+                         ((!a->relu_mask_in && !a->relu_mask_out) || a->N % 64 == 0);
+    const int e0 = (a->bias ? kEpiBias : 0) | (a->relu ? kEpiRelu : 0) | (a->relu_mask_in ? kEpiMaskIn : 0) |
+                   (a->relu_mask_out ? kEpiMaskOut : 0);
+    const bool inst = bn2 == 256 ? (b_mn ? (e0 == 0 || e0 == kEpiMaskIn)
+                                         : (e0 == 0 || e0 == (kEpiBias | kEpiRelu) || e0 == (kEpiBias | kEpiRelu | kEpiMaskOut)))
+                                 : (bn2 == 192 && e0 == 0);
+    if (bn2 && fast_ok && inst) { TM = 2; BN = bn2; m_tiles = ceil_div(a->M, 2 * TBM); }
   }
   const int n_tiles = ceil_div(a->N, BN);
   TcParams p;
@@ -849,7 +906,7 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (rc) return rc;
   if (b_mn) mp.b_half = mp.b;
   else if ((rc = make_tmap_bf16_2d(&mp.b_half, a->B, a->K, a->N, a->ldb, BN / 2))) return rc;
-  p.cta_group = (gemm_cta_group() == 2 && m_tiles % 2 == 0) ? 2 : 1;
+  p.cta_group = (TM == 1 && gemm_cta_group() == 2 && m_tiles % 2 == 0) ? 2 : 1;
   // output through TMA when its pitch allows it (always true for the model's buffers)
   const int desz = a->d_dtype == DGPT_F32 ? 4 : 2;
   p.store_mode = kStoreDirect;
@@ -925,6 +982,23 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     }                                                                                 \
     TC_EPI(BN_, 1, 1, 0, 0)                                                           \
     return launch_cfg<BN_, 1, 1, -1, 0>(mp, p, sms, st);                              \
+  }
+  if (TM == 2) {
+    const int grid = min(p.m_tiles * p.n_tiles, sms);
+    const bool masks_ok = true;
+#define TC_TM2(BN_, B_, E_) \
+    if (BN == (BN_) && b_mn == (B_) && epi == (E_) && obf == 1 && masks_ok) \
+      return launch_one<BN_, 0, B_, (E_), 1, 1, 0, 0, 2>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
+    TC_TM2(256, 0, 0)
+    TC_TM2(256, 0, kEpiBias | kEpiRelu | kEpiMaskOut)
+    TC_TM2(256, 0, kEpiBias | kEpiRelu)
+    TC_TM2(256, 1, 0)
+    TC_TM2(256, 1, kEpiMaskIn)
+    TC_TM2(192, 0, 0)
+    TC_TM2(192, 1, 0)
+#undef TC_TM2
+    set_error("gemm_tc: internal: no 256-row instantiation for BN=%d b_mn=%d epi=%d", BN, b_mn, epi);
+    return DGPT_E_ARG;
   }
   if (BN == 192) {  // single-CTA tiles only; the instantiations the N = 384 GEMMs of the model need, else generic
     p.cta_group = 1;

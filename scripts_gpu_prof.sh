@@ -1,12 +1,13 @@
 #!/bin/bash
-# round profile run: bench JSON, per-launch device times of one step (ncu, cold-cache/serialised: compare shares),
-# graph-replayed kernel probes, and one `ncu --set full` capture of the roofline kernel (FFN1 GEMM)
+# round-2 profile run: per-launch device times of one step (ncu launch list) and one `ncu --set full` capture per kernel family
 mkdir -p gpurun_out
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
-python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_nograph.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-python tools/gemm_probe.py > gpurun_out/gemm_probe.log 2>&1
-python tools/kernel_probe.py > gpurun_out/kernel_probe.log 2>&1
-python tools/gemm_probe.py --single ffn1_fwd > gpurun_out/gemm_single.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 1 -o gpurun_out/prof_gemm_r1 python tools/gemm_probe.py --single ffn1_fwd > gpurun_out/ncu_gemm.log 2>&1
-cat gpurun_out/bench_r1.json | cut -c1-600; cat gpurun_out/gemm_probe.log gpurun_out/kernel_probe.log
+cd "$(dirname "$0")"
+python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-table > gpurun_out/bench_nograph.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 360 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-table > gpurun_out/ncu_launch.log 2>&1
+for spec in "gemm_ffn1_dgrad:gemm_tc" "gemm_ffn1_fwd:gemm_tc" "attn_fwd:attn_fwd_tc2" "attn_bwd:attn_bwd_tc" "ln_bwd:ln_bwd_stream" "ln_fwd:ln_fwd_rows" "adamw:adamw_kernel" "lmhead_ce:lmhead_ce" "decode_attn:decode_attn" "decode_persistent:decode_persistent"; do
+  t=${spec%%:*}; k=${spec##*:}
+  python tools/ncu_target.py $t > gpurun_out/ncu_plain_$t.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/r2_$t python tools/ncu_target.py $t > gpurun_out/ncu_$t.log 2>&1
+  echo "$t rc=$?"
+done
+ls -la gpurun_out/*.ncu-rep

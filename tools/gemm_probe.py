@@ -30,7 +30,7 @@ shapes = {  # name: (M, N, K, a_major, b_major, out dtype, epilogue)
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 single = "--single" in sys.argv
 which = args or list(shapes)
-R = 6
+R = int(os.environ.get('GEMM_PROBE_R', '6'))  # operand / output sets (1: everything L2-resident)
 
 
 def splits(rows, cols, k, sm=148):
