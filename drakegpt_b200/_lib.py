@@ -18,7 +18,7 @@ EXPORTS = [
     "dgpt_dropout_keep_host", "dgpt_gemm_set_cta_group", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
     "dgpt_embed_bwd", "dgpt_embed_ln_fwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
     "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_lmhead_ce", "dgpt_lmhead_ce_supported", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
-    "dgpt_ipc_export", "dgpt_ipc_open", "dgpt_ipc_close", "dgpt_dp_adamw",
+    "dgpt_ipc_export", "dgpt_ipc_open", "dgpt_ipc_close", "dgpt_peer_copy", "dgpt_dp_adamw",
     "dgpt_decode_attn", "dgpt_decode_persistent", "dgpt_decode_persistent_scratch_floats",
     "dgpt_decode_persistent_max_batch",
 ]
@@ -99,6 +99,7 @@ def _declare(lib):
         "dgpt_ipc_export": [vp, vp, C.POINTER(C.c_int64)],
         "dgpt_ipc_open": [vp, i64, C.POINTER(C.c_void_p)],
         "dgpt_ipc_close": [vp, i64],
+        "dgpt_peer_copy": [vp, vp, i64, vp],
         "dgpt_dp_adamw": [C.POINTER(C.c_void_p), i32, i32, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp],
         "dgpt_sample": [vp, i32, vp, i64, i32, i32, i32, i32, u64, vp, u32, vp],
     }

@@ -34,6 +34,7 @@ struct DpPeers {
   float* p[kMaxRanks];            // parameter arena of every rank
   __nv_bfloat16* sh[kMaxRanks];   // bf16 shadow arena of every rank (may be all NULL)
   uint32_t* flags[kMaxRanks];     // flag array of every rank: [2][kMaxRanks] uint32 (A and B barriers)
+  const uint8_t* need32;          // per 64-element block of the arena: peers need the fp32 value (NULL: all blocks)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -116,10 +117,13 @@ dp_adamw_kernel(DpPeers pe, float* __restrict__ m, float* __restrict__ v, int64_
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&l2);
     pk.y = *reinterpret_cast<uint32_t*>(&h2);
+    // GEMM weights are only ever read through their bf16 shadows during training: their fp32 masters stay with the
+    // owner (need32 = 0 for those blocks; PeerAdamW.sync_master() fetches them one-sidedly for checkpoints)
+    const bool all32 = pe.need32 == nullptr || pe.need32[i >> 6] != 0;
 #pragma unroll
     for (int r = 0; r < kMaxRanks; ++r)
       if (r < world) {
-        *reinterpret_cast<float4*>(pe.p[r] + i) = pp;
+        if (all32 || r == me) *reinterpret_cast<float4*>(pe.p[r] + i) = pp;
         if (pe.sh[r]) *reinterpret_cast<uint2*>(pe.sh[r] + i) = pk;
       }
   }
@@ -203,6 +207,20 @@ int dgpt_ipc_open(const void* handle, int64_t offset, void** ptr_out) {
   return DGPT_OK;
 }
 
+/* bytes from a peer-mapped (or local) device buffer into a local one, on the stream (one-sided fetch over NVLink) */
+int dgpt_peer_copy(void* dst, const void* src, int64_t bytes, void* stream) {
+  DGPT_DEVICE_OR_RETURN();
+  DGPT_REQUIRE(dst && src && bytes >= 0, "peer_copy: bad arguments");
+  if (bytes == 0) return DGPT_OK;
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("peer_copy: %s", cudaGetErrorString(e));
+    return DGPT_E_LAUNCH;
+  }
+  return DGPT_OK;
+}
+
 int dgpt_ipc_close(void* ptr, int64_t offset) {
   if (!ptr) return DGPT_OK;
   cudaError_t e = cudaIpcCloseMemHandle((char*)ptr - offset);
@@ -214,7 +232,8 @@ int dgpt_ipc_close(void* ptr, int64_t offset) {
   return DGPT_OK;
 }
 
-// peers: host array of 4 * world device pointers: g[world], p[world], shadow[world] (entries may be NULL), flags[world];
+// peers: host array of 4 * world + 1 device pointers: g[world], p[world], shadow[world] (entries may be NULL),
+// flags[world], then need32 (uint8 per 64-element block of the arena, or NULL = broadcast every fp32 value);
 // entry [me] of each group is this rank's own buffer.  m / v: this rank's moment shards ([hi - lo] floats).
 // epoch (device uint32): barrier generation, bumped by this call (on the stream) after the kernel.
 // scratch (device, 2 x uint32, zero-initialised once): [0] block counter, [1] status (0 ok, 1 / 2 = a peer never
@@ -235,6 +254,8 @@ int dgpt_dp_adamw(const void* const* peers, int world, int me, float* m, float* 
     pe.flags[r] = (uint32_t*)peers[3 * world + r];
     DGPT_REQUIRE(pe.g[r] && pe.p[r] && pe.flags[r], "dp_adamw: missing peer pointer for rank %d", r);
   }
+  pe.need32 = (const uint8_t*)peers[4 * world];
+  DGPT_REQUIRE(!pe.need32 || pe.sh[me], "dp_adamw: need32 (bf16-only broadcast) requires the shadow arenas");
   if (sms <= 0) sms = dgpt_sm_count();
   if (sms <= 0) sms = 148;
   cudaStream_t st = (cudaStream_t)stream;

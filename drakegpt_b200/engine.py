@@ -345,7 +345,12 @@ class Runner:
         # DGPT_DP_MODE=nccl selects the NCCL all-reduce + replicated AdamW schedule (A/B, or no peer access)
         if (self.opt is not None and dist.is_initialized() and dist.get_world_size(group) > 1
                 and dist.get_backend(group) == "nccl" and os.environ.get("DGPT_DP_MODE", "peer") == "peer"):
-            return PeerAdamW(self.flat, self.opt, group)
+            sp = self.spec
+            only_shadow = [sp["lm"][0]] if self.mode == "bf16" else []
+            if self.mode == "bf16":
+                for L in sp["layers"]:  # the GEMM weights: read through their bf16 shadows only
+                    only_shadow += [L["qkv"], L["proj"][0], L["ffn"][1], L["ffn"][3]]
+            return PeerAdamW(self.flat, self.opt, group, shadow_only=only_shadow)
         nl = len(self.spec["layers"])
         groups = [("lm_head.",)] + [(f"blocks.{i}.",) for i in range(nl - 1, -1, -1)]
         groups.append(("token_embedding_table.", "position_embedding_table."))

@@ -18,6 +18,8 @@ class GraphedTrainStep:
         self.idx = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
         self.targets = torch.zeros((batch_size, seq_len), device=dev, dtype=torch.int64)
         flat, opt = runner.flat, runner.opt
+        self.reducer = reducer
+        self._lazy_master = reducer is not None and getattr(reducer, "need32", None) is not None
         opt.upload()
         keep = [t.clone() for t in (flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev)]
         side = torch.cuda.Stream(device=dev)
@@ -34,6 +36,8 @@ class GraphedTrainStep:
         for dst, src in zip((flat.p, flat.m, flat.v, opt.step_dev, runner.seed_dev), keep):
             dst.copy_(src)
         flat.g.zero_()
+        if reducer is not None and getattr(reducer, "fused_optimizer", False):
+            reducer.master_stale = False  # every rank restored its own complete copy: nothing to fetch from peers
         flat.refresh_shadow(force=True)  # bf16 shadows follow the restored fp32 masters
         torch.cuda.synchronize(dev)
 
@@ -44,6 +48,8 @@ class GraphedTrainStep:
             self.targets.copy_(targets, non_blocking=True)
         self.graph.replay()
         self.runner.opt.t += 1
+        if self._lazy_master:  # the replayed fused optimizer step left the peers' fp32 masters behind (see PeerAdamW.sync_master)
+            self.reducer.master_stale = True
         return self.loss
 
 

@@ -59,6 +59,7 @@ class FlatParams:
                 view.copy_(p.data)
                 p.data = view
         self._versions = None
+        self.before_refresh = None  # set by parallel.PeerAdamW: fetch fp32 masters owned by other ranks before a re-cast
         self.n_params = sum(k for (_, k, _) in self.slots.values())
 
     # ---- views ------------------------------------------------------------
@@ -93,6 +94,8 @@ class FlatParams:
             return
         vers = tuple(p._version for p in self.params.values())
         if force or vers != self._versions:
+            if self.before_refresh is not None:
+                self.before_refresh()
             ops.raw_cast_bf16(self.p, self.shadow)
             self._versions = vers
 

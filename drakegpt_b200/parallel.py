@@ -127,7 +127,11 @@ class PeerAdamW:
 
     fused_optimizer = True
 
-    def __init__(self, flat, opt, group=None):
+    def __init__(self, flat, opt, group=None, shadow_only=()):
+        """``shadow_only``: names of parameters that the training step reads ONLY through their bf16 shadows (the
+        tensor-core GEMM weights).  Their updated fp32 masters are not broadcast (2/3 of the outbound NVLink bytes):
+        every rank keeps them current for its own shard only and ``sync_master()`` fetches the rest on demand
+        (checkpoints, ``state_dict``).  DGPT_DP_BCAST=all broadcasts every fp32 value instead."""
         import ctypes as C
         from . import _lib
         self.flat, self.opt, self.group = flat, opt, group
@@ -139,6 +143,14 @@ class PeerAdamW:
         self.flags = torch.zeros(16, device=dev, dtype=torch.int32)
         self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
         self.scratch = torch.zeros(2, device=dev, dtype=torch.int32)
+        self.need32 = None
+        if shadow_only and flat.shadow is not None and os.environ.get("DGPT_DP_BCAST", "shadow") != "all":
+            need = torch.ones((flat.n_total + 63) // 64, dtype=torch.uint8)
+            for name in shadow_only:
+                o, k, _ = flat.slots[name]
+                need[o // 64:(o + k + 63) // 64] = 0  # (slots are 64-element aligned: a block belongs to one tensor)
+            self.need32 = need.to(dev)
+        self.master_stale = False
         lib = _lib.lib()
         mine = []
         self._local = [flat.g, flat.p, flat.shadow, self.flags]
@@ -154,7 +166,8 @@ class PeerAdamW:
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self._opened = []
-        ptrs = (C.c_void_p * (4 * self.world))()
+        self._peer_p = [None] * self.world
+        ptrs = (C.c_void_p * (4 * self.world + 1))()
         for r in range(self.world):
             for k in range(4):
                 if r == self.rank:
@@ -167,9 +180,13 @@ class PeerAdamW:
                     _lib.check(lib.dgpt_ipc_open(handle, off, C.byref(out)), "dgpt_ipc_open")
                     self._opened.append((out.value, off))
                     ptrs[k * self.world + r] = out.value
+                    if k == 1:
+                        self._peer_p[r] = out.value
+        ptrs[4 * self.world] = None if self.need32 is None else self.need32.data_ptr()
         self._ptrs = ptrs
         opt.grad_scale = 1.0 / self.world
         opt.upload()
+        flat.before_refresh = self.sync_master  # a shadow re-cast must not read stale fp32 masters
         dist.barrier(group=group)  # every rank has mapped every buffer before any kernel touches them
 
     @property
@@ -191,6 +208,25 @@ class PeerAdamW:
                                             o.step_dev.data_ptr(), self.epoch.data_ptr(), self.scratch.data_ptr(), 0,
                                             ops._stream()), "dgpt_dp_adamw")
         f.g[:f.n_live].zero_()
+        if self.need32 is not None:
+            self.master_stale = True
+
+    def sync_master(self):
+        """Fetch the fp32 masters this rank does not own from their owners' arenas (one-sided peer copies over NVLink;
+        no collective: any rank may call it alone, e.g. rank 0 before ``state_dict()``).  The caller makes sure no rank
+        is inside a training step (a ``dist.barrier()`` after the last step)."""
+        if not self.master_stale:
+            return
+        from . import _lib
+        stream = torch.cuda.current_stream(self.flat.device).cuda_stream
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            lo, hi = shard_range(self.flat.n_live, self.world, r)
+            _lib.check(_lib.lib().dgpt_peer_copy(self.flat.p.data_ptr() + 4 * lo, self._peer_p[r] + 4 * lo, 4 * (hi - lo), stream),
+                       "dgpt_peer_copy")
+        torch.cuda.current_stream(self.flat.device).synchronize()
+        self.master_stale = False
 
     def status(self):
         """0 = ok; 1 / 2 = a peer never reached the first / second barrier of some step (host sync)."""

@@ -140,6 +140,9 @@ def training_state(model, runner, opt, it, sched_steps, batcher=None, reducer=No
     moments of its own shard only: pass the ``reducer`` and call this on EVERY rank (it gathers them)."""
     flat = runner.flat
     if reducer is not None and getattr(reducer, "fused_optimizer", False):
+        import torch.distributed as dist
+        dist.barrier()            # no rank is inside a step any more
+        reducer.sync_master()     # fp32 masters owned by other ranks (only their bf16 shadows are broadcast per step)
         adam_m, adam_v = reducer.gather_moments()
     else:
         adam_m, adam_v = flat.m.detach().cpu().clone(), flat.v.detach().cpu().clone()
@@ -295,6 +298,10 @@ def main(argv=None):
                 torch.save(st, path)
                 print(f"saved training state {path} at iteration {it + 1}")
 
+    if reducer is not None and getattr(reducer, "fused_optimizer", False):
+        import torch.distributed as dist
+        dist.barrier()
+        reducer.sync_master()  # before state_dict(): fetch the fp32 masters this rank does not own
     if rank == 0:
         model.eval()
         if args.generate > 0:

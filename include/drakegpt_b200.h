@@ -269,9 +269,13 @@ int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n,
  *   dgpt_ipc_export / dgpt_ipc_open / dgpt_ipc_close: map a peer process's
  *     device buffer (handle = 64-byte cudaIpcMemHandle_t of the allocation,
  *     offset = position of the buffer inside it).
- *   peers: HOST array of 4*world device pointers -- g[world], p[world],
+ *   peers: HOST array of 4*world + 1 device pointers -- g[world], p[world],
  *     shadow[world] (may be NULL), flags[world] (each 16 x uint32, zeroed
- *     once); entry [me] of each group is this rank's own buffer.
+ *     once); entry [me] of each group is this rank's own buffer; the last
+ *     entry is need32: one byte per 64-element block of the arena, non-zero
+ *     where peers need the fp32 value (biases, LayerNorm, embeddings), zero for
+ *     blocks that are only read through their bf16 shadows (GEMM weights: the
+ *     fp32 master then stays with the owner), or NULL = broadcast everything.
  *   m, v: this rank's Adam moment shards ([hi - lo] floats); [lo, hi) is the
  *     64-element aligned shard of the arena this rank owns.
  *   hyper / step as dgpt_adamw (grad_scale = 1 / world for the mean);
@@ -283,6 +287,7 @@ int dgpt_adamw(float* p, float* g, float* m, float* v, void* shadow, int64_t n,
 int dgpt_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out);
 int dgpt_ipc_open(const void* handle, int64_t offset, void** ptr_out);
 int dgpt_ipc_close(void* ptr, int64_t offset);
+int dgpt_peer_copy(void* dst, const void* src, int64_t bytes, void* stream); /* one-sided fetch from a mapped peer buffer */
 int dgpt_dp_adamw(const void* const* peers, int world, int me, float* m, float* v, int64_t lo,
                   int64_t hi, const float* hyper, int64_t* step, uint32_t* epoch,
                   uint32_t* scratch, int sms, void* stream);

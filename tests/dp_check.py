@@ -32,6 +32,13 @@ def run(model_sd, batches, world, rank, graphed):
     torch.cuda.synchronize()
     if red is not None and getattr(red, "fused_optimizer", False):
         assert red.status() == 0, f"peer barrier timed out (status {red.status()})"
+        lazy = red.need32 is not None
+        if lazy:  # fp32 masters of the GEMM weights are only current on their owner until sync_master()
+            assert red.master_stale
+            dist.barrier()
+            red.sync_master()
+            assert not red.master_stale
+            assert torch.equal(r.flat.shadow[:r.flat.n_live].float(), r.flat.p[:r.flat.n_live].bfloat16().float())
         mom_m, mom_v = red.gather_moments()  # full-length moments assembled from the shards
         assert mom_m.shape == (r.flat.n_live,) and torch.isfinite(mom_v).all() and float(mom_v.abs().sum()) > 0
         red.close()
