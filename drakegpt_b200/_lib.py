@@ -17,7 +17,7 @@ EXPORTS = [
     "dgpt_last_error", "dgpt_abi_version", "dgpt_device_check", "dgpt_sm_count", "dgpt_debug_clock_probe", "dgpt_debug_clock_stamps",
     "dgpt_dropout_keep_host", "dgpt_gemm_set_cta_group", "dgpt_dropout_scale", "dgpt_cast_bf16", "dgpt_embed_fwd",
     "dgpt_embed_bwd", "dgpt_embed_ln_fwd", "dgpt_ln_fwd", "dgpt_ln_bwd", "dgpt_gemm", "dgpt_colsum", "dgpt_attn_fwd",
-    "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_lmhead_ce", "dgpt_lmhead_ce_supported", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
+    "dgpt_attn_bwd", "dgpt_attn_bwd_scratch_bytes", "dgpt_cross_entropy", "dgpt_lmhead_ce", "dgpt_lmhead_ce_supported", "dgpt_gemm_res_ln", "dgpt_gemm_res_ln_supported", "dgpt_adamw", "dgpt_counter_add", "dgpt_sample",
     "dgpt_ipc_export", "dgpt_ipc_open", "dgpt_ipc_close", "dgpt_peer_copy", "dgpt_dp_adamw",
     "dgpt_decode_attn", "dgpt_decode_persistent", "dgpt_decode_persistent_scratch_floats",
     "dgpt_decode_persistent_max_batch",
@@ -91,6 +91,8 @@ def _declare(lib):
         "dgpt_cross_entropy": [vp, i32, vp, vp, vp, i32, i32, vp, i32, i32, vp],
         "dgpt_lmhead_ce": [vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp],
         "dgpt_lmhead_ce_supported": [i32, i32],
+        "dgpt_gemm_res_ln": [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, i32, f32, f32, u64, vp, u32, vp],
+        "dgpt_gemm_res_ln_supported": [i32, i32],
         "dgpt_adamw": [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp],
         "dgpt_counter_add": [vp, u64, vp],
         "dgpt_decode_attn": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, f32, vp],

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdrakegpt_b200.so")
-SOURCES = ["runtime.cu", "elementwise.cu", "gemm_simt.cu", "attn_simt.cu", "gemm_tc.cu", "attn_tc.cu", "lmhead_ce.cu", "dp_adamw.cu", "decode.cu", "api.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "gemm_simt.cu", "attn_simt.cu", "gemm_tc.cu", "attn_tc.cu", "lmhead_ce.cu", "gemm_ln.cu", "dp_adamw.cu", "decode.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xcompiler", "-fvisibility=default"]

@@ -31,12 +31,18 @@ __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w 
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // ---------------------------------------------------------------------------
-// batched decode attention (any batch): one warp per (sequence, head)
+// batched decode attention (any batch): WPU warps per (sequence, head), keys split between them
 //
 // Lane mapping: 8 lanes share one key (lane & 7 = which 16-byte chunk of its 128-byte row), 4 keys per warp
 // instruction (lane >> 3).  A load instruction therefore touches 4 full 128-byte lines -- 4 L1 wavefronts -- where
 // one-key-per-lane touched 32 lines with 16 bytes each (32 wavefronts: that version ran at the L1 wavefront rate,
-// 2.5 TB/s of KV bytes, not at HBM speed).  Scores live in shared memory (nk <= 256 per warp).
+// 2.5 TB/s of KV bytes, not at HBM speed).
+// A warp walks its key range in chunks of 32 with an ONLINE softmax: the 8 K rows and the 8 V rows of a chunk are
+// requested together (8 KB in flight per warp, one memory round trip per chunk instead of a score pass followed by
+// a value pass), and the WPU partial (max, sum, output) triples of a (sequence, head) are merged through shared
+// memory.  WPU (1 / 2 / 4 / 8) is chosen by the host: as many warps as it takes to fill the machine once, never more
+// than there are 32-key chunks.  The previous version (a score pass into shared memory, then a value pass, 4 KB in
+// flight per warp, 4 CTAs per SM = 1.3 waves at batch 1024) ran at 0.53-0.67 of HBM; this one at 0.86-0.93.
 // ---------------------------------------------------------------------------
 struct DecAttnP {
   const __nv_bfloat16 *q, *k, *v;
@@ -51,15 +57,19 @@ __device__ __forceinline__ float dot8q(const uint4& w, const float (&q)[8]) {
          q[5] * bf16_hi(w.z) + q[6] * bf16_lo(w.w) + q[7] * bf16_hi(w.w);
 }
 
-__global__ void __launch_bounds__(kDecThreads, 4) decode_attn_kernel(DecAttnP p) {
+template <int WPU>
+__global__ void __launch_bounds__(kDecThreads, 2) decode_attn_kernel(DecAttnP p) {
   pdl_grid_sync();
-  __shared__ float sc_s[kDecThreads / 32][256];
+  constexpr int kWarps = kDecThreads / 32, kUnits = kWarps / WPU;
+  __shared__ float part_s[kWarps][kDecH + 2];  // per warp: running max, sum of exp, unnormalised output[64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int bh = blockIdx.x * (kDecThreads / 32) + w;
-  if (bh >= p.B * p.NH) return;
-  const int b = bh / p.NH, h = bh % p.NH;
+  const int bh = blockIdx.x * kUnits + w / WPU, wi = w % WPU;
+  const bool live = bh < p.B * p.NH;
+  const int b = live ? bh / p.NH : 0, h = live ? bh % p.NH : 0;
   const int g = lane >> 3, c = lane & 7;
-  float* sc = sc_s[w];
+  const int nk = p.nk;
+  const int per = ((nk + WPU - 1) / WPU + 3) & ~3;  // keys per warp
+  const int j_lo = wi * per, j_hi = live ? min(nk, j_lo + per) : 0;
   float q[8];
   {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.q + b * p.q_bs + h * kDecH) + c);
@@ -68,72 +78,87 @@ __global__ void __launch_bounds__(kDecThreads, 4) decode_attn_kernel(DecAttnP p)
   }
   const __nv_bfloat16* kb = p.k + b * p.k_bs + h * kDecH;
   const __nv_bfloat16* vb = p.v + b * p.v_bs + h * kDecH;
-  const int nk = p.nk;
-  // ---- scores: 8 warp iterations (32 keys) in flight at a time ----
-  float mx = -INFINITY;
-  for (int j0 = 0; j0 < nk; j0 += 32) {
-    uint4 wv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = j0 + i * 4 + g;
-      wv[i] = (j < nk) ? __ldg(reinterpret_cast<const uint4*>(kb + (int64_t)j * p.k_rs) + c) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float d = dot8q(wv[i], q);
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      const int j = j0 + i * 4 + g;
-      if (j < nk) {
-        mx = fmaxf(mx, d);
-        if (c == 0) sc[j] = d;
-      }
-    }
-  }
-  mx = warp_max(mx);
-  __syncwarp();
-  float sum = 0.f;
-  for (int j = lane; j < nk; j += 32) {
-    const float e = __expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  const float inv = 1.f / sum;
-  // ---- weighted values: lane (g, c) accumulates dims [8 c, 8 c + 8) over its keys, then the 4 groups are added ----
+  float mx = -INFINITY, sum = 0.f;  // sum: this lane group's keys only (added over the 4 groups at the end)
   float o[8];
 #pragma unroll
   for (int d = 0; d < 8; ++d) o[d] = 0.f;
-  for (int j0 = 0; j0 < nk; j0 += 32) {
-    uint4 wv[8];
+  for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+    uint4 kr[8], vr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = j0 + i * 4 + g;
-      wv[i] = (j < nk) ? __ldg(reinterpret_cast<const uint4*>(vb + (int64_t)j * p.v_rs) + c) : make_uint4(0u, 0u, 0u, 0u);
+      kr[i] = (j < j_hi) ? DEC_LD(reinterpret_cast<const uint4*>(kb + (int64_t)j * p.k_rs) + c) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = j0 + i * 4 + g;
-      const float pj = (j < nk) ? sc[j] : 0.f;
-      o[0] += pj * bf16_lo(wv[i].x); o[1] += pj * bf16_hi(wv[i].x); o[2] += pj * bf16_lo(wv[i].y); o[3] += pj * bf16_hi(wv[i].y);
-      o[4] += pj * bf16_lo(wv[i].z); o[5] += pj * bf16_hi(wv[i].z); o[6] += pj * bf16_lo(wv[i].w); o[7] += pj * bf16_hi(wv[i].w);
+      vr[i] = (j < j_hi) ? DEC_LD(reinterpret_cast<const uint4*>(vb + (int64_t)j * p.v_rs) + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float sc[8], cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float d = dot8q(kr[i], q);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      sc[i] = (j0 + i * 4 + g < j_hi) ? d : -INFINITY;
+      cm = fmaxf(cm, sc[i]);
+    }
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));  // chunk maximum, warp-uniform (key j0 is always valid: finite)
+    const float nm = fmaxf(mx, cm), rs = __expf(mx - nm);
+    mx = nm;
+    sum *= rs;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] *= rs;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float pj = __expf(sc[i] - nm);
+      sum += pj;
+      o[0] += pj * bf16_lo(vr[i].x); o[1] += pj * bf16_hi(vr[i].x); o[2] += pj * bf16_lo(vr[i].y); o[3] += pj * bf16_hi(vr[i].y);
+      o[4] += pj * bf16_lo(vr[i].z); o[5] += pj * bf16_hi(vr[i].z); o[6] += pj * bf16_lo(vr[i].w); o[7] += pj * bf16_hi(vr[i].w);
     }
   }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
     o[d] += __shfl_xor_sync(0xffffffffu, o[d], 8);
     o[d] += __shfl_xor_sync(0xffffffffu, o[d], 16);
-    o[d] *= inv;
   }
+  if (WPU == 1) {
+    if (g == 0 && live) {
+      const float inv = 1.f / sum;
+      __nv_bfloat162 a = __floats2bfloat162_rn(o[0] * inv, o[1] * inv), b2 = __floats2bfloat162_rn(o[2] * inv, o[3] * inv);
+      __nv_bfloat162 c2 = __floats2bfloat162_rn(o[4] * inv, o[5] * inv), d2 = __floats2bfloat162_rn(o[6] * inv, o[7] * inv);
+      uint4 out;
+      out.x = *reinterpret_cast<uint32_t*>(&a); out.y = *reinterpret_cast<uint32_t*>(&b2);
+      out.z = *reinterpret_cast<uint32_t*>(&c2); out.w = *reinterpret_cast<uint32_t*>(&d2);
+      reinterpret_cast<uint4*>(p.o + b * p.o_bs + h * kDecH)[c] = out;
+    }
+    return;
+  }
+  // ---- merge the WPU partial results of this (sequence, head): warp wi == 0, lane -> output dims 2 lane, 2 lane + 1 ----
+  if (lane == 0) { part_s[w][0] = mx; part_s[w][1] = sum; }
   if (g == 0) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b2 = __floats2bfloat162_rn(o[2], o[3]);
-    __nv_bfloat162 c2 = __floats2bfloat162_rn(o[4], o[5]), d2 = __floats2bfloat162_rn(o[6], o[7]);
-    uint4 out;
-    out.x = *reinterpret_cast<uint32_t*>(&a); out.y = *reinterpret_cast<uint32_t*>(&b2);
-    out.z = *reinterpret_cast<uint32_t*>(&c2); out.w = *reinterpret_cast<uint32_t*>(&d2);
-    reinterpret_cast<uint4*>(p.o + b * p.o_bs + h * kDecH)[c] = out;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) part_s[w][2 + c * 8 + d] = o[d];
+  }
+  __syncthreads();
+  if (wi == 0 && live) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < WPU; ++u) M = fmaxf(M, part_s[w + u][0]);
+    float L = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < WPU; ++u) {
+      const float f = __expf(part_s[w + u][0] - M);  // a warp without keys holds (-inf, 0, 0): f = 0
+      L += f * part_s[w + u][1];
+      a0 += f * part_s[w + u][2 + 2 * lane];
+      a1 += f * part_s[w + u][3 + 2 * lane];
+    }
+    const float inv = 1.f / L;
+    reinterpret_cast<__nv_bfloat162*>(p.o + b * p.o_bs + h * kDecH)[lane] = __floats2bfloat162_rn(a0 * inv, a1 * inv);
   }
 }
 
@@ -576,7 +601,23 @@ int dgpt_decode_attn(const void* q, const void* k, const void* v, void* o, int64
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (__nv_bfloat16*)o;
   p.q_bs = q_bs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs;
   p.B = B; p.NH = NH; p.nk = nk; p.scale = scale;
-  launch_pdl(decode_attn_kernel, dim3(ceil_div((int64_t)B * NH, kDecThreads / 32)), dim3(kDecThreads), 0, (cudaStream_t)stream, p);
+  const int64_t units = (int64_t)B * NH;
+  static int force = -1;  // DGPT_DECODE_WPU=1|2|4|8 pins the warps per (sequence, head) (experiments)
+  if (force < 0) { const char* e = getenv("DGPT_DECODE_WPU"); force = e ? atoi(e) : 0; }
+  // enough warps for one full wave (2 CTAs of 8 warps per SM), but never more warps than 32-key chunks: at batch 1024
+  // one warp per (sequence, head) streams at 0.86-0.93 of the HBM peak and splitting only adds near-empty CTAs; at batch
+  // 64 the 384 (sequence, head) pairs need 8 warps each to cover the machine (profiles/r2_decode.txt)
+  const int cap = nk <= 32 ? 1 : nk <= 64 ? 2 : nk <= 128 ? 4 : 8;
+  int need = 1;
+  while (need < 8 && units * need < (int64_t)dgpt_sm_count() * 16) need *= 2;
+  const int wpu = force ? force : need < cap ? need : cap;
+  constexpr int kW = kDecThreads / 32;
+  switch (wpu) {
+    case 1: launch_pdl(decode_attn_kernel<1>, dim3(ceil_div(units, kW)), dim3(kDecThreads), 0, (cudaStream_t)stream, p); break;
+    case 2: launch_pdl(decode_attn_kernel<2>, dim3(ceil_div(units, kW / 2)), dim3(kDecThreads), 0, (cudaStream_t)stream, p); break;
+    case 4: launch_pdl(decode_attn_kernel<4>, dim3(ceil_div(units, kW / 4)), dim3(kDecThreads), 0, (cudaStream_t)stream, p); break;
+    default: launch_pdl(decode_attn_kernel<8>, dim3(units), dim3(kDecThreads), 0, (cudaStream_t)stream, p); break;
+  }
   return check_launch("decode_attn");
 }
 

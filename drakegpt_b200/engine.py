@@ -182,8 +182,10 @@ class Runner:
                                      a0, self.buf(tag + "mean1", (M,), torch.float32), self.buf(tag + "rstd1", (M,), torch.float32))
             else:
                 ops.raw_embed_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C))
+            ln1_done = fused0
             for li, L in enumerate(sp["layers"]):
-                x = self._layer_fwd(li, L, x, B, T, training, save, ln1_done=(fused0 and li == 0))
+                nxt = sp["layers"][li + 1] if li + 1 < len(sp["layers"]) else None
+                x, ln1_done = self._layer_fwd(li, L, x, B, T, training, save, ln1_done=ln1_done, nxt=nxt)
             xin = x
             if xin.dtype != self.at:
                 xin = ops.raw_dropout_scale(x, self.buf("x_last_at", x.shape))
@@ -216,11 +218,23 @@ class Runner:
             loss = loss.view(())
         return logits, loss
 
-    def _layer_fwd(self, li, L, x, B, T, training, save, ln1_done=False):
+    def _fuse_ln(self, M, N, K):
+        """Residual GEMM + the following LayerNorm in one kernel (dgpt_gemm_res_ln): tensor mode, full-row tiles
+        (N in {128, 256, 384}) and enough 128-row tiles to occupy the GPU; DGPT_FUSE_LN=0 keeps the two kernels,
+        DGPT_FUSE_LN=force fuses at any M (tests)."""
+        import os
+        env = os.environ.get("DGPT_FUSE_LN", "1")
+        return (self.mode == "bf16" and env != "0" and (M >= 64 * self._sm or env == "force")
+                and ops.gemm_res_ln_supported(N, K))
+
+    def _layer_fwd(self, li, L, x, B, T, training, save, ln1_done=False, nxt=None):
+        """One block; returns (output, whether blocks[li + 1].ln1 has already been applied to it)."""
         M, C = x.shape
         NH, H = L["NH"], L["H"]
         D = NH * H
         tag = (lambda n: f"L{li}.{n}") if save else (lambda n: "tmp." + n)
+        ntag = (lambda n: f"L{li + 1}.{n}") if save else (lambda n: "tmp." + n)
+        ln2_done = next_ln1_done = False
         if save:
             self._saved_x = getattr(self, "_saved_x", {})
         # ---- attention branch ----
@@ -242,8 +256,16 @@ class Runner:
                          self._drop(L["p_attn"], 4 * li, training))
         if L["proj"] is not None:
             x1 = self.buf(tag("x1"), (M, C), torch.float32)
-            self._gemm(att, self.w(L["proj"][0]), x1, bias=self.f(L["proj"][1]),
-                       dropout=self._drop(L["p"], 4 * li + 1, training), residual=x if L["residual"] else None)
+            if L["residual"] and L["ffn"] is not None and L["ln2"] is not None and self._fuse_ln(M, C, D):
+                # projection + residual + ln2 in one kernel: the fp32 row stays in TMEM for the statistics
+                ops.raw_gemm_res_ln(att, self.w(L["proj"][0]), self.f(L["proj"][1]), x, x1, self.f(L["ln2"][0]),
+                                    self.f(L["ln2"][1]), self.buf(tag("xn2"), (M, C)),
+                                    self.buf(tag("mean2"), (M,), torch.float32), self.buf(tag("rstd2"), (M,), torch.float32),
+                                    dropout=self._drop(L["p"], 4 * li + 1, training))
+                ln2_done = True
+            else:
+                self._gemm(att, self.w(L["proj"][0]), x1, bias=self.f(L["proj"][1]),
+                           dropout=self._drop(L["p"], 4 * li + 1, training), residual=x if L["residual"] else None)
         else:
             x1 = att
         # ---- feed-forward branch ----
@@ -254,7 +276,8 @@ class Runner:
                 b = self.buf(tag("xn2"), (M, C))
                 mean2 = self.buf(tag("mean2"), (M,), torch.float32)
                 rstd2 = self.buf(tag("rstd2"), (M,), torch.float32)
-                ops.raw_ln_fwd(x1, self.f(L["ln2"][0]), self.f(L["ln2"][1]), b, mean2, rstd2)
+                if not ln2_done:
+                    ops.raw_ln_fwd(x1, self.f(L["ln2"][0]), self.f(L["ln2"][1]), b, mean2, rstd2)
             elif x1.dtype != self.at:
                 b = ops.raw_dropout_scale(x1, self.buf(tag("xn2"), (M, C)))
             else:
@@ -269,11 +292,20 @@ class Runner:
                 hmask = self.buf(tag("hmask"), ((F // 32) * M,), torch.int32) if save and self._use_relu_mask(F) else None
                 self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True, relu_mask_out=hmask)
                 out = self.buf(tag("x2"), (M, C), torch.float32)
-                self._gemm(h, self.w(L["ffn"][3]), out, bias=self.f(L["ffn"][4]),
-                           dropout=self._drop(L["p"], 4 * li + 2, training), residual=x1 if L["residual"] else None)
+                if L["residual"] and nxt is not None and nxt["ln1"] is not None and self._fuse_ln(M, C, F):
+                    # FFN2 + residual + the NEXT block's ln1 in one kernel
+                    ops.raw_gemm_res_ln(h, self.w(L["ffn"][3]), self.f(L["ffn"][4]), x1, out, self.f(nxt["ln1"][0]),
+                                        self.f(nxt["ln1"][1]), self.buf(ntag("xn1"), (M, C)),
+                                        self.buf(ntag("mean1"), (M,), torch.float32),
+                                        self.buf(ntag("rstd1"), (M,), torch.float32),
+                                        dropout=self._drop(L["p"], 4 * li + 2, training))
+                    next_ln1_done = True
+                else:
+                    self._gemm(h, self.w(L["ffn"][3]), out, bias=self.f(L["ffn"][4]),
+                               dropout=self._drop(L["p"], 4 * li + 2, training), residual=x1 if L["residual"] else None)
         if save:
             self._saved_x[li] = x
-        return out
+        return out, next_ln1_done
 
     # ------------------------------------------------------------------ #
     # backward (TransformerLM / ResidualBlock2 structure)

@@ -264,6 +264,24 @@ def raw_lmhead_ce(x, w, bias, targets=None, loss_sum=None, dlogits=None, logits=
                                     _stream()), "dgpt_lmhead_ce")
 
 
+def gemm_res_ln_supported(N, K):
+    return bool(_lib.lib().dgpt_gemm_res_ln_supported(int(N), int(K)))
+
+
+def raw_gemm_res_ln(a, w, bias, residual, x_out, gamma, beta, y, mean, rstd, eps=1e-5, dropout=None):
+    """x_out = dropout(a @ w^T + bias) + residual (fp32); y = LayerNorm(x_out) * gamma + beta (bf16); see
+    dgpt_gemm_res_ln.  a bf16 [M,K], w bf16 [N,K]."""
+    _need_cuda(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    dp, seed, site, seed_dev = 0.0, 0, 0, None
+    if dropout is not None and dropout.p > 0.0:
+        dp, seed, site, seed_dev = dropout.p, dropout.seed, dropout.site, dropout.seed_dev
+    check(_lib.lib().dgpt_gemm_res_ln(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual), residual.stride(0),
+                                      _p(x_out), x_out.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0), _p(mean),
+                                      _p(rstd), M, N, K, eps, dp, seed, _p(seed_dev), site, _stream()), "dgpt_gemm_res_ln")
+
+
 def raw_adamw(p, g, m, v, shadow, hyper, step, zero_grad=True, n=None):
     n = p.numel() if n is None else n
     check(_lib.lib().dgpt_adamw(_p(p), _p(g), _p(m), _p(v), _p(shadow), n, _p(hyper), _p(step), int(zero_grad),

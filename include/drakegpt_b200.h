@@ -242,6 +242,28 @@ int dgpt_lmhead_ce(const void* x, int ldx, const void* w, int ldw, const float* 
                    void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Residual GEMM with the next LayerNorm folded into its epilogue (tensor mode).
+ * Replaces the tail of one transformer sub-block and the head of the next,
+ * src/model_component.py:505-506 (x = x + sa(ln1(x)); x = x + ffwd(ln2(x))):
+ *   x_out[M, N] (fp32) = dropout(a[M, K] @ w[N, K]^T + bias) + residual[M, N]
+ *   y[M, N] (bf16) = (x_out - mean) * rstd * gamma + beta;  mean, rstd: [M]
+ * a: bf16 [M, lda]; w: bf16 [N, ldw] (nn.Linear weight); residual / x_out:
+ * fp32 with row pitches ldr / ldx; y: bf16 [M, ldy].  One CTA per 128 rows
+ * holds the whole fp32 row in TMEM (tcgen05 128 x N x 16), so the statistics
+ * need no second kernel and x_out makes no second trip through HBM.
+ * Dropout (dropout_p > 0) uses the same counter-based mask as dgpt_gemm
+ * (seed + *seed_dev, site, element index m * N + n), so dgpt_gemm's backward
+ * twins regenerate it.  Needs N in {128, 256, 384} and K % 64 == 0
+ * (dgpt_gemm_res_ln_supported); other shapes use dgpt_gemm + dgpt_ln_fwd.
+ * ------------------------------------------------------------------------- */
+int dgpt_gemm_res_ln_supported(int N, int K);
+int dgpt_gemm_res_ln(const void* a, int lda, const void* w, int ldw, const float* bias,
+                     const float* residual, int ldr, float* x_out, int ldx,
+                     const float* gamma, const float* beta, void* y, int ldy, float* mean,
+                     float* rstd, int M, int N, int K, float eps, float dropout_p,
+                     uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Fused flat AdamW (decoupled decay) over one parameter arena.
  * Replaces optimizer.zero_grad() + AdamW.step(), src/train.py:149,151
  * (torch.optim.AdamW defaults eps 1e-8, weight_decay 1e-2).

@@ -59,6 +59,24 @@ def make_gemm(name, dev="cuda"):
     return lambda: ops.raw_gemm(A, Bm, out, a_major=am, b_major=bm, **kw)
 
 
+def make_gemm_ln(name, dev="cuda"):
+    """The residual GEMM `name` ("proj_fwd" / "ffn2_fwd") with the following LayerNorm in its epilogue."""
+    m, n, k = GEMM_SHAPES[name][:3]
+    A = torch.randn(m, k, device=dev).bfloat16()
+    W = torch.randn(n, k, device=dev).bfloat16()
+    res, out = torch.randn(m, n, device=dev), torch.empty(m, n, device=dev)
+    bias, g, b = torch.zeros(n, device=dev), torch.ones(n, device=dev), torch.zeros(n, device=dev)
+    y = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(m, device=dev), torch.empty(m, device=dev)
+    drop = ops.Dropout(0.2, 1, 1)
+    return lambda: ops.raw_gemm_res_ln(A, W, bias, res, out, g, b, y, mean, rstd, dropout=drop)
+
+
+def gemm_ln_bytes(name):
+    m, n, k = GEMM_SHAPES[name][:3]
+    return 2.0 * (m * k + n * k) + m * n * (4 + 4 + 2.0) + 8.0 * m  # operands, residual in, x_out + bf16 y out, stats
+
+
 def gemm_flops(name):
     m, n, k = GEMM_SHAPES[name][:3]
     return 2.0 * m * n * k
@@ -174,6 +192,12 @@ def kernel_family_table(pk):
         tf = gemm_flops(name) / us / 1e6
         rows.append({"kernel": "gemm_" + name, "us": round(us, 2), "bound": "tensor", "achieved": round(tf, 1),
                      "unit": "TFLOP/s", "frac": round(tf / pk["bf16_burst"], 3)})
+        torch.cuda.empty_cache()
+    for name in ("proj_fwd", "ffn2_fwd"):  # the same GEMMs with the next LayerNorm folded in (what the step launches)
+        us = time_launches([make_gemm_ln(name) for _ in range(R)])
+        gb = gemm_ln_bytes(name) / us / 1e3
+        rows.append({"kernel": "gemm_ln_" + name, "us": round(us, 2), "bound": "hbm", "achieved": round(gb, 1), "unit": "GB/s",
+                     "frac": round(gb / pk["hbm"], 3), "tflops": round(gemm_flops(name) / us / 1e6, 1)})
         torch.cuda.empty_cache()
     sets = [attn_set(0.2) for _ in range(R)]
     for nm, i, fl in (("attn_fwd", 0, ATTN_FLOPS_FWD), ("attn_bwd", 1, ATTN_FLOPS_BWD)):
