@@ -242,9 +242,17 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tmem_ld32(row_addr + n + 32, r1);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        r0[j] = __float_as_uint((__uint_as_float(r0[j]) - mean) * rstd * gamma_s[n + j] + beta_s[n + j]);
-        r1[j] = __float_as_uint((__uint_as_float(r1[j]) - mean) * rstd * gamma_s[n + 32 + j] + beta_s[n + 32 + j]);
+      for (int j = 0; j < 32; j += 4) {  // (float4 broadcast reads: a quarter of the shared-memory wavefronts of scalar ones)
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma_s + n + j), b0 = *reinterpret_cast<const float4*>(beta_s + n + j);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma_s + n + 32 + j), b1 = *reinterpret_cast<const float4*>(beta_s + n + 32 + j);
+        r0[j] = __float_as_uint((__uint_as_float(r0[j]) - mean) * rstd * g0.x + b0.x);
+        r0[j + 1] = __float_as_uint((__uint_as_float(r0[j + 1]) - mean) * rstd * g0.y + b0.y);
+        r0[j + 2] = __float_as_uint((__uint_as_float(r0[j + 2]) - mean) * rstd * g0.z + b0.z);
+        r0[j + 3] = __float_as_uint((__uint_as_float(r0[j + 3]) - mean) * rstd * g0.w + b0.w);
+        r1[j] = __float_as_uint((__uint_as_float(r1[j]) - mean) * rstd * g1.x + b1.x);
+        r1[j + 1] = __float_as_uint((__uint_as_float(r1[j + 1]) - mean) * rstd * g1.y + b1.y);
+        r1[j + 2] = __float_as_uint((__uint_as_float(r1[j + 2]) - mean) * rstd * g1.z + b1.z);
+        r1[j + 3] = __float_as_uint((__uint_as_float(r1[j + 3]) - mean) * rstd * g1.w + b1.w);
       }
       uint8_t* wr = tile + lane * 128;
 #pragma unroll

@@ -1,5 +1,5 @@
 """One kernel family launched a few times, eagerly, for `ncu -k regex:... -s 2 -c 1` captures.
-    python tools/ncu_target.py gemm_ffn1_dgrad | gemm_ffn1_fwd | attn_fwd | attn_bwd | ln_fwd | ln_bwd | adamw |
+    python tools/ncu_target.py gemm_ffn1_dgrad | gemm_ffn1_fwd | gemm_ln_proj_fwd | gemm_ln_ffn2_fwd | attn_fwd | attn_bwd | ln_fwd | ln_bwd | adamw |
                                lmhead_ce | decode_attn | decode_persistent
 L2 is flushed between launches (a 256 MB memset), so the captured launch reads its operands from HBM."""
 import os
@@ -12,7 +12,9 @@ from drakegpt_b200 import ops  # noqa: E402
 
 what = sys.argv[1]
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
-if what.startswith("gemm_"):
+if what.startswith("gemm_ln_"):
+    fn = probes.make_gemm_ln(what[8:])
+elif what.startswith("gemm_"):
     fn = probes.make_gemm(what[5:])
 elif what in ("attn_fwd", "attn_bwd"):
     f, b = probes.attn_set(0.2)
