@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(512) embed_bwd_tok_smem_kernel(const int64_t* 
   for (int i = threadIdx.x; i < V; i += blockDim.x) hit[i] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) {  // ids up front: the row loop below is then one
-    const int v = (int)idx[r0 + i];                           // stream of independent loads, eight rows deep
+    const int v = (int)idx[r0 + i];                           // stream of independent loads, 32 rows deep
     ids[i] = v;
     hit[v] = 1;
   }
   __syncthreads();
-  constexpr int U = 8;
+  constexpr int U = 32;  // rows in flight per thread: 128 B per thread, ~48 KB per SM (8 rows ran at 0.9 TB/s)
   for (int m = r0; m < r1; m += U) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float x[U];

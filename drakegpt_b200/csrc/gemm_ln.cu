@@ -140,8 +140,8 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int et = threadIdx.x - 64;
     for (int i = et; i < N; i += 256) {
       bias_s[i] = p.bias ? p.bias[i] : 0.f;
-      gamma_s[i] = p.gamma[i];
-      beta_s[i] = p.beta[i];
+      gamma_s[i] = p.gamma ? p.gamma[i] : 1.f;  // gamma == NULL: y is the plain bf16 copy of x_out (no statistics)
+      beta_s[i] = p.gamma ? p.beta[i] : 0.f;
     }
     uint64_t seed = p.seed;
     if (p.thr && p.seed_dev) seed += *p.seed_dev;
@@ -210,10 +210,10 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tmem_st_wait();
     red_s[half * 128 + row] = sum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float mean = (red_s[row] + red_s[128 + row]) / (float)N;
+    const float mean = p.gamma ? (red_s[row] + red_s[128 + row]) / (float)N : 0.f;
     // ---- pass 2: variance around the mean ----
     float ss = 0.f;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = 0; b < nblk && p.gamma; ++b) {
       uint32_t r[32];
       tmem_ld32(row_addr + col_beg + b * 32, r);
       tmem_ld_wait();
@@ -226,8 +226,8 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     red_s[256 + half * 128 + row] = ss;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float rstd = rsqrtf((red_s[256 + row] + red_s[384 + row]) / (float)N + p.eps);
-    if (half == 0 && m < p.M) {
+    const float rstd = p.gamma ? rsqrtf((red_s[256 + row] + red_s[384 + row]) / (float)N + p.eps) : 1.f;
+    if (half == 0 && m < p.M && p.gamma) {
       p.mean[m] = mean;
       p.rstd[m] = rstd;
     }
@@ -310,7 +310,7 @@ int dgpt_gemm_res_ln(const void* a, int lda, const void* w, int ldw, const float
                      float* rstd, int M, int N, int K, float eps, float dropout_p, uint64_t seed,
                      const uint64_t* seed_dev, uint32_t site, void* stream) {
   DGPT_DEVICE_OR_RETURN();
-  DGPT_REQUIRE(M >= 0 && a && w && residual && x_out && gamma && beta && y && mean && rstd, "gemm_res_ln: bad arguments");
+  DGPT_REQUIRE(M >= 0 && a && w && residual && x_out && y && (!gamma || (beta && mean && rstd)), "gemm_res_ln: bad arguments");
   if (M == 0) return DGPT_OK;
   DGPT_REQUIRE(gemm_res_ln_supported(N, K), "gemm_res_ln: needs N in {128, 256, 384} and K %% 64 == 0 (N=%d K=%d)", N, K);
   DGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gemm_res_ln: dropout_p %g outside [0, 1)", (double)dropout_p);

@@ -183,11 +183,14 @@ class Runner:
             else:
                 ops.raw_embed_fwd(idx, tok, self.f(sp["pos"]), x.view(B, T, C))
             ln1_done = fused0
+            self._x_last_cast = None
             for li, L in enumerate(sp["layers"]):
                 nxt = sp["layers"][li + 1] if li + 1 < len(sp["layers"]) else None
                 x, ln1_done = self._layer_fwd(li, L, x, B, T, training, save, ln1_done=ln1_done, nxt=nxt)
             xin = x
-            if xin.dtype != self.at:
+            if self._x_last_cast is not None:
+                xin = self._x_last_cast  # written by the last block's fused FFN2 kernel
+            elif xin.dtype != self.at:
                 xin = ops.raw_dropout_scale(x, self.buf("x_last_at", x.shape))
             self._x_last = xin
             Cin = xin.shape[1]
@@ -292,7 +295,12 @@ class Runner:
                 hmask = self.buf(tag("hmask"), ((F // 32) * M,), torch.int32) if save and self._use_relu_mask(F) else None
                 self._gemm(b, self.w(L["ffn"][1]), h, bias=self.f(L["ffn"][2]), relu=True, relu_mask_out=hmask)
                 out = self.buf(tag("x2"), (M, C), torch.float32)
-                if L["residual"] and nxt is not None and nxt["ln1"] is not None and self._fuse_ln(M, C, F):
+                if L["residual"] and nxt is None and self.at != torch.float32 and self._fuse_ln(M, C, F):
+                    # last block: FFN2 + residual, and the bf16 copy the LM head reads, in one kernel
+                    self._x_last_cast = self.buf("x_last_at", (M, C))
+                    ops.raw_gemm_res_ln(h, self.w(L["ffn"][3]), self.f(L["ffn"][4]), x1, out, None, None,
+                                        self._x_last_cast, None, None, dropout=self._drop(L["p"], 4 * li + 2, training))
+                elif L["residual"] and nxt is not None and nxt["ln1"] is not None and self._fuse_ln(M, C, F):
                     # FFN2 + residual + the NEXT block's ln1 in one kernel
                     ops.raw_gemm_res_ln(h, self.w(L["ffn"][3]), self.f(L["ffn"][4]), x1, out, self.f(nxt["ln1"][0]),
                                         self.f(nxt["ln1"][1]), self.buf(ntag("xn1"), (M, C)),

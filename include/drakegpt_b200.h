@@ -253,7 +253,8 @@ int dgpt_lmhead_ce(const void* x, int ldx, const void* w, int ldw, const float* 
  * need no second kernel and x_out makes no second trip through HBM.
  * Dropout (dropout_p > 0) uses the same counter-based mask as dgpt_gemm
  * (seed + *seed_dev, site, element index m * N + n), so dgpt_gemm's backward
- * twins regenerate it.  Needs N in {128, 256, 384} and K % 64 == 0
+ * twins regenerate it.  gamma == NULL: no normalisation, y is the bf16 copy of
+ * x_out (the last block's output feeding the LM head); beta / mean / rstd unused.  Needs N in {128, 256, 384} and K % 64 == 0
  * (dgpt_gemm_res_ln_supported); other shapes use dgpt_gemm + dgpt_ln_fwd.
  * ------------------------------------------------------------------------- */
 int dgpt_gemm_res_ln_supported(int N, int K);
