@@ -821,8 +821,15 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   // 128 x 256 tiles ingest 25 % fewer operand bytes per MMA cycle than 128 x 128; a ragged last column
   // tile (N = 1152 -> 4.5 tiles) costs less than that as soon as N >= 1024 (TMA zero-fills, the store clips)
   int BN = 256;
-  if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024) || a->a_colsum) BN = 128;
-  if (BN == 256 && m_tiles * ceil_div(a->N, 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
+  // wgrads that carry a column sum (bias gradient): 256-column tiles when the output has few row tiles and wide rows
+  // (FFN2: 384 x 1536) -- a 128 x 128 tile needs 64 operand bytes per 1 K MMA cycles where the SM ingests ~70 B/cycle,
+  // a 128 x 256 tile 48; their single accumulator buffer costs nothing because a split-K CTA owns one tile.
+  // DGPT_GEMM_CS256=0 keeps 128-column tiles (Runner._splits reads the same variable).
+  static int cs256_env = -1;
+  if (cs256_env < 0) { const char* e = getenv("DGPT_GEMM_CS256"); cs256_env = e ? atoi(e) : 1; }
+  const bool cs_wide = cs256_env && a->a_colsum && a->N % 256 == 0 && a->N >= 512 && m_tiles < 8;
+  if (a->N <= 128 || (a->N % 256 != 0 && a->N < 1024) || (a->a_colsum && !cs_wide)) BN = 128;
+  if (BN == 256 && !cs_wide && m_tiles * ceil_div(a->N, 256) * (a->split_k > 1 ? a->split_k : 1) < sms) BN = 128;
   // 192-column tiles for N = 192, 384, 576, 960 (the model's N = 384 GEMMs): two tiles per row instead of three
   static int bn192_env = -1;
   if (bn192_env < 0) { const char* e = getenv("DGPT_GEMM_BN192"); bn192_env = e ? atoi(e) : 1; }
@@ -976,9 +983,9 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
       return launch_cfg<BN_, 0, 1, -1, 0>(mp, p, sms, st);                            \
     }                                                                                 \
     if (a->a_colsum) {                                                                \
-      DGPT_REQUIRE(BN_ == 128 && epi == 0 && obf == 0, "gemm(bf16): a_colsum needs the plain fp32 wgrad form");   \
+      DGPT_REQUIRE(epi == 0 && obf == 0, "gemm(bf16): a_colsum needs the plain fp32 wgrad form");   \
       const int total = p.m_tiles * p.n_tiles * p.split_k;                            \
-      return launch_one<128, 1, 1, 0, 0, 1, 0, 1>(mp.a, mp.b, mp.d, mp.r, p, min(total, sms), st);               \
+      return launch_one<BN_, 1, 1, 0, 0, 1, 0, 1>(mp.a, mp.b, mp.d, mp.r, p, min(total, sms), st);               \
     }                                                                                 \
     TC_EPI(BN_, 1, 1, 0, 0)                                                           \
     return launch_cfg<BN_, 1, 1, -1, 0>(mp, p, sms, st);                              \

@@ -400,9 +400,14 @@ class Runner:
         return red
 
     @staticmethod
-    def _splits(n_out_rows, n_out_cols, k, sm):
-        # column tile of the wgrad GEMM: 192 for N = 192 / 384 / 576 / 960, else 128 (launch_gemm_tc picks the same)
+    def _splits(n_out_rows, n_out_cols, k, sm, colsum=False):
+        # column tile of the wgrad GEMM: 192 for N = 192 / 384 / 576 / 960, 256 for a wide output with few row tiles that
+        # also carries a column sum (FFN2: 384 x 1536), else 128 (launch_gemm_tc picks the same)
+        import os
         bn = 192 if (n_out_cols % 192 == 0 and n_out_cols % 256 != 0 and n_out_cols < 1024 and n_out_rows >= 1024) else 128
+        if (colsum and n_out_cols % 256 == 0 and n_out_cols >= 512 and n_out_rows < 1024
+                and os.environ.get("DGPT_GEMM_CS256", "1") != "0"):
+            bn = 256
         tiles = ((n_out_rows + 127) // 128) * ((n_out_cols + bn - 1) // bn)
         return max(1, min(sm // max(tiles, 1), k // 512))
 
@@ -424,7 +429,7 @@ class Runner:
         # ---- FFN2: y = h W2^T + b2 (dropout, residual) ----
         tc = self.mode == "bf16"  # tensor mode: every bias gradient is a by-product of its wgrad GEMM
         self._gemm(gm, h, self.g(L["ffn"][3]), a_major=MAJOR_MN, b_major=MAJOR_MN, accumulate=True,
-                   split_k=self._splits(C, F, M, sm), a_colsum=self.g(L["ffn"][4]) if tc else None)
+                   split_k=self._splits(C, F, M, sm, colsum=tc), a_colsum=self.g(L["ffn"][4]) if tc else None)
         if not tc and li == len(self.spec["layers"]) - 1:  # other layers: fused into the LN1 backward of layer li+1
             ops.raw_colsum(gm, self.g(L["ffn"][4]), accumulate=True)
         dh = self.buf("dh", (M, F))

@@ -55,7 +55,8 @@ def make_gemm(name, dev="cuda"):
     elif epi == "splitk":
         kw = dict(accumulate=True, split_k=_splits(m, n, k))
     elif epi == "splitk_cs":
-        kw = dict(accumulate=True, split_k=_splits(m, n, k), a_colsum=torch.zeros(m, device=dev))
+        from drakegpt_b200.engine import Runner
+        kw = dict(accumulate=True, split_k=Runner._splits(m, n, k, ops.sm_count(), colsum=True), a_colsum=torch.zeros(m, device=dev))
     return lambda: ops.raw_gemm(A, Bm, out, a_major=am, b_major=bm, **kw)
 
 
