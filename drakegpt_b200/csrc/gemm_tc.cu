@@ -839,6 +839,23 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
   if (bn192_env && BN == 128 && a->N % 192 == 0 && a->N % 256 != 0 && a->N < 1024 && m_tiles >= 8 && !a->residual &&
       !a->relu_mask_in && !a->relu_mask_out)
     BN = 192;
+  // Wave quantisation for the big-activation GEMMs (M >= 1024 rows, no split-K): a persistent grid of `sms` CTAs walks
+  // m_tiles * n_tiles equal tiles, so 768 tiles on 148 SMs (N = 1536 with 256-column tiles) leave the last of 6 rounds
+  // 81 % empty, and N = 1152 wastes half of every fifth column tile on top.  Pick the width with the best
+  //   (useful columns / tiled columns) * (tiles / (rounds * sms)) * (tile-shape factor: 1.0 / 0.95 / 0.88 for 256 / 192 / 128,
+  // measured: operand re-reads and per-tile bookkeeping).  FFN1 fwd / FFN2 dgrad (N = 1536): 192 (1024 tiles, 6.9 rounds);
+  // QKV fwd (N = 1152): 128 (1152 tiles, 7.8 rounds).  DGPT_GEMM_WAVE=0 turns the rule off.
+  static int wave_env = -1;
+  if (wave_env < 0) { const char* e = getenv("DGPT_GEMM_WAVE"); wave_env = e ? atoi(e) : 1; }
+  if (wave_env && BN == 256 && !cs_wide && a->split_k <= 1 && m_tiles >= 8 && !a->residual && !a->a_colsum && a->N >= 1024) {
+    auto score = [&](int bn, double shape) {
+      const int nt = ceil_div(a->N, bn), tiles = m_tiles * nt, rounds = ceil_div(tiles, sms);
+      return shape * ((double)a->N / (nt * bn)) * ((double)tiles / ((double)rounds * sms));
+    };
+    double best = score(256, 1.0);
+    if (a->N % 192 == 0 && score(192, 0.95) > best) { best = score(192, 0.95); BN = 192; }
+    if (score(128, 0.88) > best) BN = 128;
+  }
   {  // DGPT_GEMM_FORCE_BN=128|256: tile-width experiments (192 only through the rule above)
     static int force = -1;
     if (force < 0) { const char* e = getenv("DGPT_GEMM_FORCE_BN"); force = e ? atoi(e) : 0; }
@@ -1014,6 +1031,9 @@ int launch_gemm_tc(const dgpt_gemm_args* a, cudaStream_t st) {
     if (a_mn == (A_) && b_mn == (B_) && epi == (E_) && obf == (O_) && (a->a_colsum != nullptr) == ((C_) != 0)) \
       return launch_one<192, A_, B_, (E_), O_, 1, R_, C_>(mp.a, mp.b, mp.d, mp.r, p, grid, st);
     TC_192(0, 0, 0, 1, 0, 0)
+    TC_192(0, 0, kEpiBias | kEpiRelu, 1, 0, 0)
+    TC_192(0, 0, kEpiBias | kEpiRelu | kEpiMaskOut, 1, 0, 0)
+    TC_192(0, 1, kEpiMaskIn, 1, 0, 0)
     TC_192(0, 1, 0, 1, 0, 0)
     TC_192(0, 1, 0, 0, 0, 0)
     TC_192(1, 1, 0, 0, 0, 0)
