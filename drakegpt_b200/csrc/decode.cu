@@ -3,13 +3,14 @@
 // Replaces the reference's `generate` loop (src/model.py:611-636: full forward over the cropped window + softmax +
 // torch.multinomial + torch.cat per token) while the window has not slid:
 //
-//   decode_attn_kernel        one new query per (sequence, head) against the cached keys / values: one warp per
-//                             (b, h), lanes over keys, 16-byte loads -- the batch-1024 end of the sweep is bound by
-//                             streaming the KV cache, so the kernel is built to keep HBM busy (8 x 16 B in flight per lane)
+//   decode_attn_kernel<WPU>   one new query per (sequence, head) against the cached keys / values: 1-8 warps per
+//                             (b, h) with the keys split between them, 8 lanes per key row, online softmax over 32-key
+//                             chunks -- the batch-1024 end of the sweep is bound by streaming the KV cache, so the kernel
+//                             is built to keep HBM busy (16 x 16 B in flight per lane: the K and V rows of a chunk)
 //   decode_persistent_kernel  small batches (<= 8 sequences): ONE launch generates every token of the in-window part.
 //                             All layers of a token run as phases of a persistent grid (LayerNorm fused into the
 //                             matrix-vector prologue, bias / ReLU / residual into its epilogue, KV append, attention,
-//                             LM head, on-device multinomial / argmax sampling) separated by grid-wide barriers;
+//                             LM head, on-device multinomial / argmax sampling) separated by cluster barriers;
 //                             the 21.6 MB of bf16 weights stay L2-resident across tokens.  The launch-per-kernel path
 //                             needs ~45 launches per token; this one needs none.
 #include <cuda.h>
