@@ -576,14 +576,18 @@ class Runner:
 
     def _persistent_decode_ok(self, Bn):
         """The one-launch persistent decoder covers the TransformerLM block structure in tensor mode, head size 64,
-        context <= 256, up to 8 sequences per 16-CTA cluster (72 on a 148-SM B200); DGPT_DECODE_PERSISTENT=0 turns it
-        off for A/B runs."""
+        context <= 256.  It is used while every sequence gets a 16-CTA cluster of its own (<= 4 sequences: 134 us per
+        token against 187-191 us for the per-position graphs); with two sequences per cluster (5-8) it measures 216 us
+        against 191-193 us, so those batches take the graph path.  DGPT_DECODE_PERSISTENT=0 turns it off,
+        DGPT_DECODE_PERSISTENT=force uses it up to the kernel's limit of 8 sequences (A/B runs, tests)."""
         import os
         from . import _lib
         sp = self.spec
-        if self.mode != "bf16" or os.environ.get("DGPT_DECODE_PERSISTENT", "1") == "0":
+        env = os.environ.get("DGPT_DECODE_PERSISTENT", "1")
+        if self.mode != "bf16" or env == "0":
             return False
-        if not (1 <= Bn <= int(_lib.lib().dgpt_decode_persistent_max_batch())):
+        limit = int(_lib.lib().dgpt_decode_persistent_max_batch())
+        if not (1 <= Bn <= (limit if env == "force" else min(limit, 4))):
             return False
         if sp["ctx"] is None or sp["ctx"] > 256 or not (1 <= len(sp["layers"]) <= 8):
             return False
@@ -663,7 +667,7 @@ class Runner:
         graphs = self.__dict__.setdefault("_decode_graphs", {})
         n_in = min(total - 1, ctx)  # positions decoded inside the window
         if self._persistent_decode_ok(Bn) and n_in > 0:
-            # small / medium batch: ONE launch (a thread-block cluster per <= 8 sequences) walks every in-window position (all layers, KV append, attention,
+            # small batch: ONE launch (a thread-block cluster per sequence) walks every in-window position (all layers, KV append, attention,
             # LM head, sampling) -- no per-token launches at all
             self._decode_persistent(seqw, caches, Bn, 0, n_in, t0 - 1, greedy, sample_seed)
             n_done = n_in
