@@ -8,7 +8,8 @@
 
 namespace dgpt {
 
-static constexpr int kSMs = 148;
+// SM count of the current device (grid sizing; 148 on B200)
+#define kSMs (dgpt_sm_count())
 
 // ---------------------------------------------------------------------------
 // dropout_scale / cast
@@ -96,7 +97,7 @@ __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __rest
 __global__ void __launch_bounds__(512) embed_bwd_tok_smem_kernel(const int64_t* __restrict__ idx,
                                                                  const float* __restrict__ dx,
                                                                  float* __restrict__ dtok, int M, int C, int V,
-                                                                 int rows_per_cta) {
+                                                                 int rows_per_cta, int bulk) {
   pdl_grid_sync();
   extern __shared__ float table[];  // [V][C], hit flags [V], then this CTA's token ids [rows_per_cta]
   int* hit = reinterpret_cast<int*>(table + (size_t)V * C);
@@ -121,6 +122,19 @@ __global__ void __launch_bounds__(512) embed_bwd_tok_smem_kernel(const int64_t* 
       for (int u = 0; u < U; ++u)
         if (m + u < r1) table[ids[m + u - r0] * C + c] += x[u];
     }
+  }
+  // flush.  16-byte aligned gradient table: ONE bulk reduction of the whole shared-memory table (rows that were not hit
+  // hold zeros) through the TMA unit -- the element-wise red.add loop below issued V * C atomics per CTA (4.5 M at the
+  // benchmark shape) and was most of this kernel's 21 us.
+  if (bulk) {
+    ptx::fence_proxy_async();  // this thread's table writes -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ptx::bulk_reduce_add_f32(dtok, table, (uint32_t)(V * C * sizeof(float)));
+      ptx::bulk_commit();
+      ptx::bulk_wait<0>();
+    }
+    return;
   }
   __syncthreads();
   for (int v = 0; v < V; ++v) {
@@ -979,7 +993,8 @@ int dgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok, float* dpos
     const int M = B * T;
     const int ctas = min(kSMs, ceil_div(M, 32));
     const int rows_per_cta = ceil_div(M, ctas);
-    launch_pdl(embed_bwd_tok_smem_kernel, dim3(ceil_div(M, rows_per_cta)), dim3(384), table_bytes, st, idx, dx, dtok, M, C, V, rows_per_cta);
+    const int bulk = (((uintptr_t)dtok & 15) == 0 && ((size_t)V * C * sizeof(float)) % 16 == 0) ? 1 : 0;
+    launch_pdl(embed_bwd_tok_smem_kernel, dim3(ceil_div(M, rows_per_cta)), dim3(384), table_bytes, st, idx, dx, dtok, M, C, V, rows_per_cta, bulk);
   } else {
     dim3 grid(V, ceil_div(C, 512));
     embed_bwd_tok_kernel<<<grid, 256, 0, st>>>(idx, dx, dtok, B * T, C);

@@ -177,6 +177,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// global[0 .. bytes) += shared[0 .. bytes) as fp32, one bulk reduction handled by the TMA unit / L2 (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N>
