@@ -604,6 +604,17 @@ __global__ void __launch_bounds__(32 + 32 * kLnRows, 1) ln_bwd_stream_kernel(
     ag[i] = ab[i] = am[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invC = 1.f / (float)C;
+  // Dropout mask of the bf16 copy.  With C % 32 == 0 a lane's float4 (quad q = lane + 32 i of the row) is always quad
+  // (lane & 7) of its 32-element mask group, so the per-element multiplier / offset of the mask generator are four
+  // per-thread constants (computed at run time they cost ~12 instructions per element), and the eight lanes that share
+  // a group take its hash from the first of them instead of hashing eight times.
+  const bool drop_fast = thr != 0;  // (the host only picks this kernel with dropout when C % 32 == 0)
+  uint32_t dmul[4], dadd[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    dmul[k] = drop_mul((uint32_t)(lane & 7) * 4u + (uint32_t)k);
+    dadd[k] = drop_add((uint32_t)(lane & 7) * 4u + (uint32_t)k);
+  }
   int s = 0;
   uint32_t ph = 0;
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -647,12 +658,15 @@ __global__ void __launch_bounds__(32 + 32 * kLnRows, 1) ln_bwd_stream_kernel(
           }
           st4(dx + ro + 4 * q, v);
           if (dxm) {
-            if (thr) {
-              const u32x4 b = dropout_bits4(seed, site, (uint64_t)row * (uint64_t)nv + (uint64_t)q);
-              v.x = b.x >= thr ? v.x * inv_keep : 0.f;
-              v.y = b.y >= thr ? v.y * inv_keep : 0.f;
-              v.z = b.z >= thr ? v.z * inv_keep : 0.f;
-              v.w = b.w >= thr ? v.w * inv_keep : 0.f;
+            if (drop_fast) {
+              // (q < nv holds for all eight lanes of a group or for none: nv % 8 == 0, so the shuffles are safe)
+              DropGroup dg = {0u, 0u};
+              if ((lane & 7) == 0) dg = dropout_group(seed, site, ((uint64_t)row * (uint64_t)nv + (uint64_t)q) >> 3);
+              const uint32_t h0 = __shfl_sync(0xffffffffu, dg.s0, lane & ~7), h1 = __shfl_sync(0xffffffffu, dg.s1, lane & ~7);
+              v.x = h0 * dmul[0] + dadd[0] >= thr ? v.x * inv_keep : 0.f;
+              v.y = h1 * dmul[1] + dadd[1] >= thr ? v.y * inv_keep : 0.f;
+              v.z = h0 * dmul[2] + dadd[2] >= thr ? v.z * inv_keep : 0.f;
+              v.w = h1 * dmul[3] + dadd[3] >= thr ? v.w * inv_keep : 0.f;
             }
             st4(dxm + ro + 4 * q, v);
             am[i].x += v.x; am[i].y += v.y; am[i].z += v.z; am[i].w += v.w;
@@ -1052,7 +1066,7 @@ int dgpt_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma
   const bool fast = (C % 4 == 0) && C <= 1024 && al(x, 16) && al(gamma, 16) && al(dx, 16) && (!dres || al(dres, 16)) &&
                     al(dy, dy_dtype == DGPT_F32 ? 16 : 8) && (!dxm || al(dxm, dxm_dtype == DGPT_F32 ? 16 : 8));
   const bool stream_ok = fast && M >= 1024 && (C * (dy_dtype == DGPT_F32 ? 4 : 2)) % 16 == 0 && al(mean, 16) &&
-                         al(rstd, 16) && al(dy, 16) && M % kLnRows == 0;
+                         al(rstd, 16) && al(dy, 16) && M % kLnRows == 0 && (thr == 0 || !dxm || C % 32 == 0);
   if (stream_ok) {
     const int dyb = dy_dtype == DGPT_F32 ? 4 : 2;
     const int stage_bytes = kLnRows * (C * dyb + 2 * C * 4) + 2 * kLnRows * 4 + 64;
