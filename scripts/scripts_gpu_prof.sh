@@ -2,7 +2,7 @@
 # round-2 profile run: per-launch device times of one step (ncu launch list) and one `ncu --set full` capture per kernel
 # family, summarised ON the GPU box (tools/ncu_summary.py) so that only text comes back (gpurun_out/ is capped at 64 MiB)
 mkdir -p gpurun_out
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-table > gpurun_out/bench_nograph.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 360 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-table > gpurun_out/ncu_launch.log 2>&1
 python tools/ncu_summary.py launches gpurun_out/r2_launches.csv > gpurun_out/r2_launches_summary.txt 2>&1
