@@ -229,3 +229,18 @@ def test_peer_optimizer_shards_tile_the_arena():
         assert max(sizes) - min(sizes) <= 64
     with pytest.raises(ValueError):
         shard_range(100, 2, 0)
+
+
+def test_wgrad_split_k_follows_the_tile_policy(monkeypatch):
+    """Runner._splits mirrors launch_gemm_tc's column-tile choice for the wgrad GEMMs (engine.py / csrc/gemm_tc.cu):
+    enough K splits to fill the SMs once, computed from the tile count the kernel will really use."""
+    from drakegpt_b200.engine import Runner
+    M, C, F, sm = 16384, 384, 1536, 148
+    assert Runner._splits(F, C, M, sm) == 6            # FFN1 wgrad: 12 row tiles x 2 tiles of 192 columns
+    assert Runner._splits(3 * C, C, M, sm) == 8        # QKV wgrad: 9 x 2
+    assert Runner._splits(C, C, M, sm) == 16           # proj wgrad: 3 x 3 tiles of 128 (few row tiles: no 192)
+    assert Runner._splits(C, F, M, sm) == 4            # FFN2 wgrad without a column sum: 3 x 12 tiles of 128
+    assert Runner._splits(C, F, M, sm, colsum=True) == 8   # with the bias gradient riding on it: 3 x 6 tiles of 256
+    monkeypatch.setenv("DGPT_GEMM_CS256", "0")
+    assert Runner._splits(C, F, M, sm, colsum=True) == 4
+    assert Runner._splits(80, C, 64, sm) == 1          # never more splits than 512-deep K slices
