@@ -274,6 +274,13 @@ def raw_gemm_res_ln(a, w, bias, residual, x_out, gamma, beta, y, mean, rstd, eps
     _need_cuda(a, w)
     M, K = a.shape
     N = w.shape[0]
+    if not (a.dtype == w.dtype == y.dtype == torch.bfloat16 and residual.dtype == x_out.dtype == torch.float32):
+        raise _lib.KernelError("gemm_res_ln: a / w / y must be bf16, residual / x_out fp32")
+    if w.shape[1] != K or residual.shape != (M, N) or x_out.shape != (M, N) or y.shape != (M, N):
+        raise _lib.KernelError(f"gemm_res_ln: shapes a {tuple(a.shape)} w {tuple(w.shape)} residual {tuple(residual.shape)} "
+                          f"x_out {tuple(x_out.shape)} y {tuple(y.shape)}")
+    if any(t.stride(-1) != 1 for t in (a, w, residual, x_out, y)):
+        raise _lib.KernelError("gemm_res_ln: operands must be contiguous along their last dimension")
     dp, seed, site, seed_dev = 0.0, 0, 0, None
     if dropout is not None and dropout.p > 0.0:
         dp, seed, site, seed_dev = dropout.p, dropout.seed, dropout.site, dropout.seed_dev
